@@ -1,0 +1,255 @@
+/*
+ * rtx.h — C ABI of the B200 ray-casting hot path (librtx_b200.so).
+ *
+ * This is the drop-in boundary for rustray's per-pixel render loop.  The reference has no
+ * FFI; the seam it replaces is the Rust call chain
+ *     RendererManager::start / start_thread      (reference src/renderer.rs:105-172, 253-318)
+ *       -> Raytracing::render(x, y) -> PixelData (reference src/raytracing.rs:275-427)
+ *       -> Run::apply_pixels (four frame buffers) (reference src/run.rs:506-545)
+ * i.e. "render this frame of this scene with this config into image / normals / depth /
+ * objects".  Every entry point below cites the reference interface it stands in for.
+ *
+ * Conventions
+ *  - plain C, no torch / CUDA types in signatures (device pointers are void*, streams void*).
+ *  - all 4x4 matrices are COLUMN-MAJOR float[16] (element (r,c) at [c*4+r]) — the in-memory
+ *    layout of nalgebra::Matrix4<f32>, so a Rust host passes `m.as_slice().as_ptr()`.
+ *  - every function returns 0 on success or a negative RTX_E_* code; the reference's
+ *    `unwrap()` panics become error codes (rtx_last_error() gives the text).
+ *  - the caller owns all input memory; rtx_scene_create copies what it needs to the device.
+ *  - frame buffers are indexed y*width+x (reference src/run.rs:118, 533-536).
+ */
+#ifndef RTX_B200_H
+#define RTX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTX_ABI_VERSION 1
+
+/* error codes */
+#define RTX_OK              0
+#define RTX_E_INVALID      -1   /* bad argument / inconsistent scene description            */
+#define RTX_E_CUDA         -2   /* CUDA runtime error (no device, OOM, launch failure)       */
+#define RTX_E_NO_DEVICE    -3   /* no CUDA device: this library has no CPU fallback          */
+#define RTX_E_NON_AFFINE   -4   /* item transform is not affine (reference would panic in
+                                   Vector3::from_homogeneous, src/shape/mod.rs:760)          */
+#define RTX_E_EMPTY_MESH   -5   /* mesh with 0 triangles (parry TriMesh::new panics)         */
+
+/* TextureType order — reference src/shape/mod.rs:633-643 */
+enum {
+    RTX_TEX_BASE = 0, RTX_TEX_AMBIENT_EMISSIVE = 1, RTX_TEX_SPECULAR = 2, RTX_TEX_NORMAL = 3,
+    RTX_TEX_ALPHA = 4, RTX_TEX_ROUGHNESS = 5, RTX_TEX_AMBIENT_OCCLUSION = 6,
+    RTX_TEX_REFLECTIVITY = 7, RTX_TEX_COUNT = 8
+};
+
+/* LightType — reference src/scene.rs:32-37 */
+enum { RTX_LIGHT_DIRECTIONAL = 0, RTX_LIGHT_POINT = 1, RTX_LIGHT_SPOT = 2 };
+
+/* shape kind — reference src/shape/sphere.rs (Sphere), src/shape/mesh.rs (Mesh) */
+enum { RTX_SHAPE_SPHERE = 0, RTX_SHAPE_MESH = 1 };
+
+/* A decoded texture: what `DynamicImage::get_pixel(x,y).to_rgba()` returns for every texel
+ * (reference src/shape/mod.rs:521-531), row-major, 4 bytes per texel. */
+typedef struct RtxTexture {
+    uint32_t width, height;
+    const uint8_t* rgba;
+} RtxTexture;
+
+/* Material — reference src/shape/mod.rs:95-134 (same field names, same defaults :137-180) */
+typedef struct RtxMaterial {
+    uint32_t id;
+    float ambient_color[3];
+    float base_color[3];
+    float specular_color[3];
+    int32_t  texture[RTX_TEX_COUNT];     /* index into RtxSceneDesc.textures, -1 = none (width 0) */
+    uint32_t texture_filtering_nearest;
+    float alpha, shininess, reflectivity, refraction_index, normal_map_strength;
+    uint32_t cast_shadow, receive_shadow;
+    float shadow_softness;
+    uint32_t monte_carlo;
+    float roughness;
+    uint32_t smooth_shading, reflection_only, backface_cullig /* sic */;
+} RtxMaterial;
+
+/* Mesh buffers — reference src/shape/mesh.rs:10-21.  uv / normal arrays may be empty. */
+typedef struct RtxMesh {
+    const float*    vertices;         /* n_vertices * 3 */
+    const uint32_t* indices;          /* n_faces * 3    */
+    const float*    uvs;              /* n_uvs * 2      */
+    const uint32_t* uv_indices;       /* n_uv_faces * 3 */
+    const float*    normals;          /* n_normals * 3  */
+    const uint32_t* normals_indices;  /* n_normal_faces * 3 */
+    uint32_t n_vertices, n_faces, n_uvs, n_uv_faces, n_normals, n_normal_faces;
+} RtxMesh;
+
+/* Item = ShapeBasics + shape payload — reference src/shape/mod.rs:661-680.
+ * `tran_inverse` is what ShapeBasics::calc_inverse stored (:763-767); the local AABB and the
+ * material cache (:33-38) are derived by the library from mesh/radius and the material. */
+typedef struct RtxItem {
+    uint32_t id;
+    uint32_t shape;          /* RTX_SHAPE_* */
+    uint32_t visible, flip_normals;
+    float trans[16];
+    float tran_inverse[16];
+    int32_t  material;       /* index into materials */
+    int32_t  mesh;           /* index into meshes (RTX_SHAPE_MESH)  */
+    float    radius;         /* Ball radius (RTX_SHAPE_SPHERE)      */
+    uint32_t reserved;
+} RtxItem;
+
+/* Light — reference src/scene.rs:40-51 */
+typedef struct RtxLight {
+    uint32_t enabled, id, light_type;
+    float pos[3], dir[3], color[3];
+    float intensity, max_angle /* rad */;
+} RtxLight;
+
+/* The flattened result of Scene::load* + init + update (reference src/scene.rs:121-157,
+ * 1666-1688).  Item order == scene.items order (it decides shadow first-hit ties). */
+typedef struct RtxSceneDesc {
+    const RtxItem*     items;      uint32_t n_items;
+    const RtxMesh*     meshes;     uint32_t n_meshes;
+    const RtxMaterial* materials;  uint32_t n_materials;
+    const RtxTexture*  textures;   uint32_t n_textures;
+    const RtxLight*    lights;     uint32_t n_lights;
+} RtxSceneDesc;
+
+/* Camera — the two matrices Raytracing::render reads (reference src/camera.rs:34-38,79-90)
+ * plus the frame size (cam.width / cam.height). */
+typedef struct RtxCamera {
+    float projection_inverse[16];
+    float view_inverse[16];
+    uint32_t width, height;
+} RtxCamera;
+
+/* RaytracingConfig — reference src/raytracing.rs:92-127 (same names, same defaults).
+ * `mc_seed` is an extension: the reference draws Monte-Carlo jitter from thread_rng()
+ * (:616-618), which is irreproducible; here it is a counter-based generator keyed on
+ * (mc_seed, pixel, sample, ray path, slot). */
+typedef struct RtxConfig {
+    uint32_t monte_carlo;
+    uint32_t samples;
+    float focal_length, aperture_size;
+    float fog_density, fog_color[3];
+    uint32_t max_recursion;
+    uint32_t gamma_correction;
+    uint32_t mc_seed;
+    uint32_t debug_flags;               /* RTX_DEBUG_* bits, 0 in production */
+} RtxConfig;
+
+#define RTX_DEBUG_COLLECT_STATS  1u   /* count node visits / primitive tests per ray (slower)        */
+#define RTX_DEBUG_ORDERED_SHADOW 2u   /* shadow rays: literal "closest hit of every item in bbox
+                                         order" walk instead of the equivalent two-phase any-hit     */
+
+/* Interleaved-tile shard of one frame: tile t (row-major over ceil(w/tile_w) x ceil(h/tile_h))
+ * belongs to rank t % world.  world = 1 renders everything. */
+typedef struct RtxShard {
+    uint32_t rank, world, tile_w, tile_h;
+} RtxShard;
+
+/* Per-frame counters.  One ray == one Raytracing::trace call (reference
+ * src/raytracing.rs:726 closest-hit, :883 shadow). */
+typedef struct RtxStats {
+    uint64_t rays_closest, rays_shadow;
+    uint64_t primary_samples;
+    uint64_t node_visits, tri_tests, sphere_tests, item_tests;  /* only with RTX_DEBUG_COLLECT_STATS */
+    uint64_t kernel_launches;
+    uint32_t waves, batches;
+    float device_ms;       /* CUDA events around all device work of the frame            */
+    float trace_ms;        /* CUDA events, closest-hit + shadow traversal kernels only    */
+    float shade_ms;        /* CUDA events, raygen + shade + resolve kernels               */
+    uint64_t h2d_bytes, d2h_bytes;
+} RtxStats;
+
+typedef struct RtxRay { float origin[3]; float dir[3]; } RtxRay;
+/* Result of Raytracing::trace: Option<(f32, Vector3, &dyn Shape, u32)> (src/raytracing.rs:429) */
+typedef struct RtxHit {
+    float t;              /* < 0  => None */
+    float normal[3];
+    uint32_t item_id;     /* ShapeBasics.id, 0 on miss */
+    uint32_t face_id;     /* parry FeatureId::Face index (+n_faces on a backface), 0 for spheres */
+    int32_t  item_index;  /* position in RtxSceneDesc.items, -1 on miss */
+    uint32_t reserved;
+} RtxHit;
+
+typedef struct RtxBvhInfo {
+    uint32_t n_nodes, n_triangles, n_items, tlas_nodes;
+    uint64_t node_bytes, triangle_bytes, item_bytes, texture_bytes;
+    float build_ms;
+} RtxBvhInfo;
+
+typedef struct RtxScene RtxScene;   /* opaque */
+
+/* Scene::load + init + update, flattened (reference src/scene.rs:121-157,1674-1688): copies the
+ * description, builds the per-mesh wide BVHs and the item-level structure, uploads to
+ * `device` (CUDA ordinal).  Fails with RTX_E_NO_DEVICE when there is no GPU. */
+int rtx_scene_create(const RtxSceneDesc* desc, int device, RtxScene** out);
+
+/* Scene::apply_frame / ShapeBasics::apply_mat + Scene::update (reference src/scene.rs:1695-1713,
+ * src/shape/mod.rs:748-753,1674-1688): replace transforms of n items (by position in items). */
+typedef struct RtxItemXform { uint32_t item_index; float trans[16]; float tran_inverse[16]; } RtxItemXform;
+int rtx_scene_update_items(RtxScene* scene, const RtxItemXform* xforms, size_t n);
+
+/* Replace lights / one material's scalar fields between frames (GUI editors, src/run.rs). */
+int rtx_scene_set_lights(RtxScene* scene, const RtxLight* lights, uint32_t n_lights);
+
+/* RendererManager::start .. is_done + every Run::apply_pixels write (reference
+ * src/renderer.rs:105-172,228; src/run.rs:506-545).  Blocking.  HOST output buffers:
+ * rgba w*h*4 (a = 255, run.rs:527), normals w*h*3, depth w*h, object_ids w*h.
+ * Any output pointer may be NULL.  `stats` may be NULL. */
+int rtx_render_frame(RtxScene* scene, const RtxCamera* cam, const RtxConfig* cfg,
+                     uint8_t* rgba, float* normals, float* depth, uint32_t* object_ids,
+                     RtxStats* stats);
+
+/* Same frame, DEVICE output buffers (same layouts) on the scene's device, restricted to the
+ * pixels of `shard` (NULL = whole frame); pixels of other ranks are left untouched.
+ * Work is enqueued on `cuda_stream` (a cudaStream_t, NULL = default stream) and the call
+ * returns after the stream has drained (the wavefront loop reads queue sizes back). */
+int rtx_render_frame_device(RtxScene* scene, const RtxCamera* cam, const RtxConfig* cfg,
+                            const RtxShard* shard,
+                            void* d_rgba, void* d_normals, void* d_depth, void* d_object_ids,
+                            void* cuda_stream, RtxStats* stats);
+
+/* Multi-GPU gather helpers: pack the owned pixels of a shard into a compact device buffer
+ * (layout: n*4 rgba bytes | n*3 normal floats | n depth floats | n id uint32, n =
+ * rtx_shard_pixel_count) and scatter such a buffer (from any rank) into full frame buffers. */
+uint64_t rtx_shard_pixel_count(uint32_t width, uint32_t height, const RtxShard* shard);
+uint64_t rtx_shard_packed_bytes(uint32_t width, uint32_t height, const RtxShard* shard);
+int rtx_shard_pack(uint32_t width, uint32_t height, const RtxShard* shard,
+                   const void* d_rgba, const void* d_normals, const void* d_depth,
+                   const void* d_object_ids, void* d_packed, void* cuda_stream);
+int rtx_shard_unpack(uint32_t width, uint32_t height, const RtxShard* shard,
+                     const void* d_packed, void* d_rgba, void* d_normals, void* d_depth,
+                     void* d_object_ids, void* cuda_stream);
+
+/* Raytracing::trace (reference src/raytracing.rs:429-490) and, with for_shadow = 0 on a
+ * primary ray, Raytracing::pick (:237-273).  HOST arrays of n rays / n hits.  Ray directions
+ * are used as given (the callers in the reference normalise first, :262,:723). */
+int rtx_trace_probe(RtxScene* scene, const RtxRay* rays, size_t n, int for_shadow,
+                    int stop_on_first_hit, uint32_t depth, RtxHit* hits);
+
+/* The per-pixel sample sub-grid of Raytracing::render (reference src/raytracing.rs:290-313):
+ * cell_size, and `samples` (x_i, y_i) pairs after StdRng::seed_from_u64(0) shuffle + truncate.
+ * xy must hold 2*samples uint16. */
+int rtx_sample_table(uint32_t samples, uint32_t* cell_size, uint16_t* xy);
+
+int rtx_scene_bvh_info(const RtxScene* scene, RtxBvhInfo* info);
+int rtx_scene_destroy(RtxScene* scene);
+const char* rtx_last_error(void);
+int rtx_abi_version(void);
+int rtx_device_count(void);
+
+/* Post-processing on the finished G-buffer (reference src/post_processing.rs:77-181), device
+ * side, in place on d_rgba.  cavity/outline as in PostProcessingConfig. */
+int rtx_post_process_device(uint32_t width, uint32_t height, int cavity, int outline,
+                            void* d_rgba, const void* d_normals, const void* d_depth,
+                            const void* d_object_ids, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTX_B200_H */

@@ -1,0 +1,828 @@
+// rtx_api.cu — C ABI (include/rtx.h) of the B200 ray-casting path: scene flattening + BVH upload,
+// the host side of the wavefront loop, the probe hook and the shard helpers.
+//
+// Wavefront scheduling.  Rays live in per-depth queues (depth 1 .. max_recursion+1), each with room
+// for 3*CHUNK rays.  One "wave" pops <= CHUNK rays from the tail of one queue and runs
+//   closest_kernel -> shade_kernel (appends <= 2 children per ray to the next queue and one shadow
+//   ray per enabled light) -> shadow_kernel
+// then reads the two appended counts back (one 16-byte D2H).  The queue to pop is the deepest one
+// holding >= CHUNK rays, else a fresh batch of primary rays, else the shallowest non-empty queue;
+// that keeps every queue below 3*CHUNK without ever dropping or re-queueing a ray, and keeps waves
+// fat (a deep queue is only drained early when it is full).
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/rtx.h"
+#include "bvh_build.h"
+#include "rtx_kernels.cuh"
+
+using namespace rtx;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CU(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            g_err = std::string(#expr) + ": " + cudaGetErrorString(e__);                           \
+            return RTX_E_CUDA;                                                                     \
+        }                                                                                          \
+    } while (0)
+
+constexpr uint32_t kLinearItems = 16;     // item loop instead of a TLAS up to this many items
+constexpr uint32_t kCtrPool = 1u << 16;   // counters (4 per wave) zeroed in one memset
+
+inline bool approx_equal_h(float a, float b) { return std::trunc(a * 1000000.0f) == std::trunc(b * 1000000.0f); }
+
+template <typename T> struct DevBuf {
+    T* p = nullptr; size_t n = 0;
+    int alloc(size_t count) {
+        if (count <= n && p) return RTX_OK;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        if (count == 0) return RTX_OK;
+        CU(cudaMalloc(&p, count * sizeof(T)));
+        n = count;
+        return RTX_OK;
+    }
+    int upload(const std::vector<T>& v, cudaStream_t s = 0) {
+        int rc = alloc(std::max<size_t>(v.size(), 1));
+        if (rc) return rc;
+        if (!v.empty()) CU(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+        return RTX_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct PixelList { DevBuf<uint32_t> d; uint32_t n = 0; };
+
+}  // namespace
+
+struct RtxScene {
+    int device = 0; int sm_count = 148;
+    // host mirrors needed for updates
+    std::vector<RtxItem> src_items; std::vector<DItem> h_items; std::vector<RtxMaterial> src_mats;
+    std::vector<uint32_t> mesh_root; std::vector<RtxMesh> mesh_meta;
+    uint32_t n_blas_nodes = 0, n_tris = 0, tlas_cap = 0, n_tlas_nodes = 0;
+    size_t texture_bytes = 0; float build_ms = 0.f;
+    // device scene
+    DevBuf<float4> nodes, tris; DevBuf<DItem> items; DevBuf<uint32_t> tlas_prims;
+    DevBuf<float> verts, uvs, nrms; DevBuf<uint32_t> idx, uv_idx, n_idx;
+    DevBuf<DMaterial> mats; DevBuf<DTex> texs; DevBuf<uchar4> texels; DevBuf<DLight> lights;
+    SceneDev dev{};
+    // frame state
+    DevBuf<float4> accum_c, accum_n; DevBuf<uint32_t> ids; size_t frame_pixels = 0;
+    std::map<std::tuple<uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t>, PixelList*> pixel_lists;
+    DevBuf<ushort2> sample_table; uint32_t table_samples = 0, cell_size = 1;
+    // queues
+    uint32_t chunk = 0, levels = 0, level_cap = 0, shadow_cap = 0;
+    DevBuf<float4> q_o, q_d; DevBuf<uint2> q_m;
+    DevBuf<float4> s_o, s_d, s_c; DevBuf<uint32_t> s_r;
+    DevBuf<HitRec> hits; DevBuf<uint32_t> ctr_pool; DevBuf<uint32_t> overflow; DevBuf<Counters> counters;
+    uint32_t* h_ctr = nullptr;              // pinned, 4 uint32
+    std::vector<cudaEvent_t> events;
+    int blocks_closest = 0, blocks_closest_st = 0, blocks_shadow = 0, blocks_shadow_st = 0, blocks_shadow_ord = 0;
+    // host-output staging for rtx_render_frame
+    DevBuf<uchar4> o_rgba; DevBuf<float> o_normals, o_depth; DevBuf<uint32_t> o_ids;
+    // probe staging
+    DevBuf<ProbeRay> p_rays; DevBuf<ProbeHit> p_hits;
+};
+
+namespace {
+
+// ---- scene flattening -----------------------------------------------------------------------------
+void fill_item(const RtxScene& sc, const RtxItem& s, DItem& d) {
+    memset(&d, 0, sizeof(d));
+    for (int r = 0; r < 3; r++) {
+        d.inv[r] = make_float4(s.tran_inverse[0 + r], s.tran_inverse[4 + r], s.tran_inverse[8 + r], s.tran_inverse[12 + r]);
+        d.mat[r] = make_float4(s.trans[0 + r], s.trans[4 + r], s.trans[8 + r], s.trans[12 + r]);
+    }
+    const RtxMaterial& m = sc.src_mats[s.material];
+    // material cache = Material::new + apply_diff_without_textures (reference src/shape/mod.rs:182-246,769-772)
+    const float c_alpha = approx_equal_h(1.0f, m.alpha) ? 1.0f : m.alpha;
+    uint32_t f = 0;
+    if (s.shape == RTX_SHAPE_MESH) f |= IF_MESH;
+    if (s.visible) f |= IF_VISIBLE;
+    if (s.flip_normals) f |= IF_FLIP;
+    if (m.cast_shadow) f |= IF_CAST_SHADOW;
+    if (m.reflection_only) f |= IF_REFL_ONLY;
+    if (m.backface_cullig) f |= IF_BACKFACE;
+    if (m.smooth_shading) f |= IF_SMOOTH;
+    if (c_alpha > 0.0f) f |= IF_ALPHA_POS;
+    if (c_alpha < 1.0f) f |= IF_ALPHA_LT1;
+    if (m.texture[RTX_TEX_ALPHA] >= 0) f |= IF_ALPHA_TEX;
+    d.id = s.id; d.material = (uint32_t)s.material;
+    d.lo.w = s.radius; d.hi.w = c_alpha;
+    d.flags = f;
+}
+
+void item_world_box(const DItem& d, Aabb3& b) {
+    const float inf = INFINITY;
+    b = {{inf, inf, inf}, {-inf, -inf, -inf}};
+    const float lo[3] = {d.lo.x, d.lo.y, d.lo.z}, hi[3] = {d.hi.x, d.hi.y, d.hi.z};
+    for (int c = 0; c < 8; c++) {
+        const float p[3] = {(c & 1) ? hi[0] : lo[0], (c & 2) ? hi[1] : lo[1], (c & 4) ? hi[2] : lo[2]};
+        const float4 rows[3] = {d.mat[0], d.mat[1], d.mat[2]};
+        for (int r = 0; r < 3; r++) {
+            float v = rows[r].x * p[0] + rows[r].y * p[1] + rows[r].z * p[2] + rows[r].w;
+            float pad = std::fabs(v) * 1e-6f + 1e-30f;                 // the TLAS is only a conservative filter
+            b.lo[r] = std::min(b.lo[r], v - pad); b.hi[r] = std::max(b.hi[r], v + pad);
+        }
+    }
+}
+
+void append_nodes(std::vector<float4>& out, const WideBvh& bvh, uint32_t node_off, uint32_t prim_off) {
+    for (const WideNode& wn : bvh.nodes) {
+        WideNode n = wn;
+        n.child_base += node_off; n.prim_base += prim_off;
+        float4 f[5]; memcpy(f, &n, 80);
+        for (int k = 0; k < 5; k++) out.push_back(f[k]);
+    }
+}
+
+int build_tlas(RtxScene& sc, std::vector<float4>& tlas_nodes, std::vector<uint32_t>& tlas_prims) {
+    std::vector<Aabb3> boxes(sc.h_items.size());
+    for (size_t i = 0; i < sc.h_items.size(); i++) item_world_box(sc.h_items[i], boxes[i]);
+    WideBvh bvh; build_wide_bvh(boxes.data(), (uint32_t)boxes.size(), bvh);
+    if (bvh.max_depth > 14) return fail(RTX_E_INVALID, "TLAS too deep");
+    tlas_nodes.clear();
+    append_nodes(tlas_nodes, bvh, sc.n_blas_nodes, 0);
+    tlas_prims = bvh.prim_order;
+    sc.n_tlas_nodes = (uint32_t)bvh.nodes.size();
+    return RTX_OK;
+}
+
+void fill_lights(const RtxLight* l, uint32_t n, std::vector<DLight>& out) {
+    out.resize(n);
+    for (uint32_t i = 0; i < n; i++) {
+        DLight d; memset(&d, 0, sizeof(d));
+        memcpy(d.pos, l[i].pos, 12); memcpy(d.dir, l[i].dir, 12); memcpy(d.color, l[i].color, 12);
+        d.type = l[i].light_type; d.intensity = l[i].intensity; d.max_angle = l[i].max_angle; d.enabled = l[i].enabled;
+        out[i] = d;
+    }
+}
+
+void refresh_dev(RtxScene& sc) {
+    SceneDev& D = sc.dev;
+    D.nodes = sc.nodes.p; D.tris = sc.tris.p; D.items = sc.items.p; D.tlas_prims = sc.tlas_prims.p;
+    D.verts = sc.verts.p; D.idx = sc.idx.p; D.uvs = sc.uvs.p; D.uv_idx = sc.uv_idx.p; D.nrms = sc.nrms.p; D.n_idx = sc.n_idx.p;
+    D.mats = sc.mats.p; D.texs = sc.texs.p; D.texels = sc.texels.p; D.lights = sc.lights.p;
+    D.n_items = (uint32_t)sc.h_items.size();
+    D.tlas_root = sc.n_blas_nodes; D.use_tlas = sc.h_items.size() > kLinearItems ? 1u : 0u;
+    D.ball_flip_inside = 1u;
+}
+
+int get_pixel_list(RtxScene& sc, uint32_t w, uint32_t h, const RtxShard* shard, PixelList** out) {
+    RtxShard sh = shard ? *shard : RtxShard{0, 1, 8, 4};
+    if (sh.world == 0 || sh.rank >= sh.world || sh.tile_w == 0 || sh.tile_h == 0) return fail(RTX_E_INVALID, "bad shard");
+    auto key = std::make_tuple(w, h, sh.rank, sh.world, sh.tile_w, sh.tile_h);
+    auto it = sc.pixel_lists.find(key);
+    if (it != sc.pixel_lists.end()) { *out = it->second; return RTX_OK; }
+    std::vector<uint32_t> px;
+    const uint32_t tx = (w + sh.tile_w - 1) / sh.tile_w, ty = (h + sh.tile_h - 1) / sh.tile_h;
+    for (uint32_t t = sh.rank; t < tx * ty; t += sh.world) {
+        const uint32_t x0 = (t % tx) * sh.tile_w, y0 = (t / tx) * sh.tile_h;
+        for (uint32_t y = y0; y < std::min(y0 + sh.tile_h, h); y++)
+            for (uint32_t x = x0; x < std::min(x0 + sh.tile_w, w); x++) px.push_back(y * w + x);
+    }
+    PixelList* pl = new PixelList();
+    pl->n = (uint32_t)px.size();
+    int rc = pl->d.upload(px);
+    if (rc) { delete pl; return rc; }
+    sc.pixel_lists[key] = pl;
+    *out = pl;
+    return RTX_OK;
+}
+
+// rand 0.8 StdRng (ChaCha12) + seed_from_u64 + SliceRandom::shuffle — reference src/raytracing.rs:300-313
+struct StdRng12 {
+    uint32_t key[8]; uint64_t counter = 0; uint32_t buf[16]; int idx = 16;
+    static uint32_t rotl(uint32_t v, int c) { return (v << c) | (v >> (32 - c)); }
+    explicit StdRng12(uint64_t state) {
+        for (int i = 0; i < 8; i++) {                                 // PCG32 seed expansion
+            state = state * 6364136223846793005ull + 11634580027462260723ull;
+            uint32_t xs = (uint32_t)(((state >> 18) ^ state) >> 27), rot = (uint32_t)(state >> 59);
+            key[i] = (xs >> rot) | (xs << ((32 - rot) & 31));
+        }
+    }
+    void block() {
+        uint32_t s[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key[0], key[1], key[2], key[3], key[4], key[5], key[6], key[7],
+                          (uint32_t)counter, (uint32_t)(counter >> 32), 0u, 0u};
+        uint32_t x[16]; memcpy(x, s, 64);
+        auto qr = [&](int a, int b, int c, int d) {
+            x[a] += x[b]; x[d] = rotl(x[d] ^ x[a], 16); x[c] += x[d]; x[b] = rotl(x[b] ^ x[c], 12);
+            x[a] += x[b]; x[d] = rotl(x[d] ^ x[a], 8);  x[c] += x[d]; x[b] = rotl(x[b] ^ x[c], 7);
+        };
+        for (int i = 0; i < 6; i++) { qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15); qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14); }
+        for (int i = 0; i < 16; i++) buf[i] = x[i] + s[i];
+        counter++; idx = 0;
+    }
+    uint32_t next() { if (idx >= 16) block(); return buf[idx++]; }
+    uint32_t below(uint32_t range) {                                   // UniformInt<u32>::sample_single
+        uint32_t zone = (range << __builtin_clz(range)) - 1u;
+        for (;;) { uint64_t m = (uint64_t)next() * range; if ((uint32_t)m <= zone) return (uint32_t)(m >> 32); }
+    }
+};
+void make_sample_table(uint32_t samples, uint32_t& cell, std::vector<ushort2>& out) {
+    cell = 1;
+    if (samples > 1) { uint32_t v = (samples + 2) & 0xFFFFu, p = 1; while (p < v) p <<= 1; cell = p / 2; }
+    std::vector<ushort2> s; s.reserve((size_t)cell * cell);
+    for (uint32_t x = 0; x < cell; x++) for (uint32_t y = 0; y < cell; y++) s.push_back(make_ushort2((unsigned short)x, (unsigned short)y));
+    StdRng12 rng(0);
+    for (size_t i = s.size() - 1; i >= 1; i--) std::swap(s[i], s[rng.below((uint32_t)(i + 1))]);
+    if (s.size() > samples) s.resize(samples);
+    out = s;
+}
+
+int ensure_frame(RtxScene& sc, uint32_t w, uint32_t h) {
+    size_t n = (size_t)w * h;
+    int rc;
+    if ((rc = sc.accum_c.alloc(n)) || (rc = sc.accum_n.alloc(n)) || (rc = sc.ids.alloc(n))) return rc;
+    sc.frame_pixels = n;
+    return RTX_OK;
+}
+
+int ensure_queues(RtxScene& sc, uint32_t max_recursion, uint32_t n_lights_enabled) {
+    uint32_t levels = max_recursion + 1;
+    if (levels > 64) return fail(RTX_E_INVALID, "max_recursion > 63 is not supported by the wavefront queues");
+    uint32_t chunk = 1u << 21;
+    if (const char* e = getenv("RTX_CHUNK")) { long v = atol(e); if (v >= 1024) chunk = (uint32_t)v; }
+    while (levels > 12 && chunk > (1u << 17) && (size_t)levels * 3 * chunk * 40 > (size_t)8 << 30) chunk >>= 1;
+    uint32_t shadow_cap = chunk * std::max(1u, n_lights_enabled);
+    if (sc.chunk == chunk && sc.levels >= levels && sc.shadow_cap >= shadow_cap) return RTX_OK;
+    sc.chunk = chunk; sc.levels = std::max(sc.levels, levels); sc.level_cap = 3 * chunk; sc.shadow_cap = std::max(sc.shadow_cap, shadow_cap);
+    size_t qn = (size_t)sc.levels * sc.level_cap;
+    int rc;
+    if ((rc = sc.q_o.alloc(qn)) || (rc = sc.q_d.alloc(qn)) || (rc = sc.q_m.alloc(qn))) return rc;
+    if ((rc = sc.s_o.alloc(sc.shadow_cap)) || (rc = sc.s_d.alloc(sc.shadow_cap)) || (rc = sc.s_c.alloc(sc.shadow_cap)) || (rc = sc.s_r.alloc(sc.shadow_cap))) return rc;
+    if ((rc = sc.hits.alloc(chunk)) || (rc = sc.ctr_pool.alloc(kCtrPool)) || (rc = sc.overflow.alloc(1)) || (rc = sc.counters.alloc(1))) return rc;
+    if (!sc.h_ctr) CU(cudaMallocHost(&sc.h_ctr, 16));
+    return RTX_OK;
+}
+
+int occupancy_blocks(RtxScene& sc) {
+    if (sc.blocks_closest) return RTX_OK;
+    int b = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, closest_kernel<false>, kTraceBlock, 0)); sc.blocks_closest = std::max(1, b) * sc.sm_count;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, closest_kernel<true>, kTraceBlock, 0)); sc.blocks_closest_st = std::max(1, b) * sc.sm_count;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, shadow_kernel<false, false>, kTraceBlock, 0)); sc.blocks_shadow = std::max(1, b) * sc.sm_count;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, shadow_kernel<true, false>, kTraceBlock, 0)); sc.blocks_shadow_st = std::max(1, b) * sc.sm_count;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, shadow_kernel<false, true>, kTraceBlock, 0)); sc.blocks_shadow_ord = std::max(1, b) * sc.sm_count;
+    return RTX_OK;
+}
+
+RayQ level_queue(RtxScene& sc, uint32_t level /*1-based depth*/) {
+    size_t off = (size_t)(level - 1) * sc.level_cap;
+    return RayQ{sc.q_o.p + off, sc.q_d.p + off, sc.q_m.p + off};
+}
+
+}  // namespace
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+const char* rtx_last_error(void) { return g_err.c_str(); }
+int rtx_abi_version(void) { return RTX_ABI_VERSION; }
+int rtx_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
+
+int rtx_sample_table(uint32_t samples, uint32_t* cell_size, uint16_t* xy) {
+    if (samples == 0 || samples > 65535) return fail(RTX_E_INVALID, "samples out of range");
+    uint32_t cell; std::vector<ushort2> t; make_sample_table(samples, cell, t);
+    if (cell_size) *cell_size = cell;
+    if (xy) for (size_t i = 0; i < t.size(); i++) { xy[2 * i] = t[i].x; xy[2 * i + 1] = t[i].y; }
+    return RTX_OK;
+}
+
+int rtx_scene_create(const RtxSceneDesc* d, int device, RtxScene** out) {
+    if (!d || !out) return fail(RTX_E_INVALID, "null argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(RTX_E_NO_DEVICE, "no CUDA device: librtx_b200 has no CPU fallback"); }
+    if (device < 0 || device >= ndev) return fail(RTX_E_INVALID, "bad device ordinal");
+    CU(cudaSetDevice(device));
+    auto t0 = std::chrono::steady_clock::now();
+    RtxScene* sc = new RtxScene();
+    sc->device = device;
+    cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, device)); sc->sm_count = prop.multiProcessorCount;
+    auto bail = [&](int code, const std::string& m) { rtx_scene_destroy(sc); return fail(code, m); };
+
+    // ---- validate + copy ----
+    for (uint32_t i = 0; i < d->n_items; i++) {
+        const RtxItem& it = d->items[i];
+        if (it.material < 0 || (uint32_t)it.material >= d->n_materials) return bail(RTX_E_INVALID, "item material index out of range");
+        if (it.shape == RTX_SHAPE_MESH && (it.mesh < 0 || (uint32_t)it.mesh >= d->n_meshes)) return bail(RTX_E_INVALID, "item mesh index out of range");
+        if (it.shape != RTX_SHAPE_MESH && it.shape != RTX_SHAPE_SPHERE) return bail(RTX_E_INVALID, "unknown shape kind");
+        // Vector3::from_homogeneous(tran_inverse * dir).unwrap() needs w == 0 (src/shape/mod.rs:760)
+        if (it.tran_inverse[3] != 0.0f || it.tran_inverse[7] != 0.0f || it.tran_inverse[11] != 0.0f || it.tran_inverse[15] != 1.0f)
+            return bail(RTX_E_NON_AFFINE, "item transform is not affine");
+    }
+    for (uint32_t i = 0; i < d->n_materials; i++)
+        for (int t = 0; t < RTX_TEX_COUNT; t++)
+            if (d->materials[i].texture[t] >= (int32_t)d->n_textures) return bail(RTX_E_INVALID, "texture index out of range");
+    sc->src_items.assign(d->items, d->items + d->n_items);
+    sc->src_mats.assign(d->materials, d->materials + d->n_materials);
+
+    // ---- meshes: BLAS per mesh ----
+    std::vector<float4> h_nodes, h_tris;
+    std::vector<float> h_verts, h_uvs, h_nrms; std::vector<uint32_t> h_idx, h_uvidx, h_nidx;
+    struct MeshOff { uint32_t vert, idx, uv, uvidx, nrm, nidx; float lo[3], hi[3]; };
+    std::vector<MeshOff> moff(d->n_meshes);
+    sc->mesh_root.resize(d->n_meshes);
+    sc->mesh_meta.assign(d->meshes, d->meshes + d->n_meshes);
+    for (uint32_t mi = 0; mi < d->n_meshes; mi++) {
+        const RtxMesh& m = d->meshes[mi];
+        if (m.n_faces == 0) return bail(RTX_E_EMPTY_MESH, "mesh with 0 triangles (parry TriMesh::new panics)");
+        for (size_t k = 0; k < 3 * (size_t)m.n_faces; k++) if (m.indices[k] >= m.n_vertices) return bail(RTX_E_INVALID, "vertex index out of range");
+        for (size_t k = 0; k < 3 * (size_t)m.n_uv_faces; k++) if (m.uv_indices[k] >= m.n_uvs) return bail(RTX_E_INVALID, "uv index out of range");
+        for (size_t k = 0; k < 3 * (size_t)m.n_normal_faces; k++) if (m.normals_indices[k] >= m.n_normals) return bail(RTX_E_INVALID, "normal index out of range");
+        if (m.n_normal_faces && m.n_normal_faces < m.n_faces) return bail(RTX_E_INVALID, "normals_indices shorter than indices");
+        MeshOff& o = moff[mi];
+        o.vert = (uint32_t)h_verts.size(); o.idx = (uint32_t)h_idx.size(); o.uv = (uint32_t)h_uvs.size();
+        o.uvidx = (uint32_t)h_uvidx.size(); o.nrm = (uint32_t)h_nrms.size(); o.nidx = (uint32_t)h_nidx.size();
+        h_verts.insert(h_verts.end(), m.vertices, m.vertices + 3 * (size_t)m.n_vertices);
+        h_idx.insert(h_idx.end(), m.indices, m.indices + 3 * (size_t)m.n_faces);
+        if (m.n_uvs) h_uvs.insert(h_uvs.end(), m.uvs, m.uvs + 2 * (size_t)m.n_uvs);
+        if (m.n_uv_faces) h_uvidx.insert(h_uvidx.end(), m.uv_indices, m.uv_indices + 3 * (size_t)m.n_uv_faces);
+        if (m.n_normals) h_nrms.insert(h_nrms.end(), m.normals, m.normals + 3 * (size_t)m.n_normals);
+        if (m.n_normal_faces) h_nidx.insert(h_nidx.end(), m.normals_indices, m.normals_indices + 3 * (size_t)m.n_normal_faces);
+        std::vector<Aabb3> boxes(m.n_faces);
+        for (int k = 0; k < 3; k++) { o.lo[k] = INFINITY; o.hi[k] = -INFINITY; }
+        for (uint32_t f = 0; f < m.n_faces; f++) {
+            Aabb3& b = boxes[f];
+            for (int k = 0; k < 3; k++) { b.lo[k] = INFINITY; b.hi[k] = -INFINITY; }
+            for (int c = 0; c < 3; c++) {
+                const float* v = m.vertices + 3 * (size_t)m.indices[3 * (size_t)f + c];
+                for (int k = 0; k < 3; k++) { b.lo[k] = std::min(b.lo[k], v[k]); b.hi[k] = std::max(b.hi[k], v[k]); }
+            }
+            for (int k = 0; k < 3; k++) { o.lo[k] = std::min(o.lo[k], b.lo[k]); o.hi[k] = std::max(o.hi[k], b.hi[k]); }   // TriMesh::aabb
+        }
+        WideBvh bvh; build_wide_bvh(boxes.data(), m.n_faces, bvh);
+        if (bvh.max_depth >= kStack - 2) return bail(RTX_E_INVALID, "BLAS too deep for the traversal stack");
+        const uint32_t node_off = (uint32_t)(h_nodes.size() / 5), tri_off = (uint32_t)(h_tris.size() / 3);
+        sc->mesh_root[mi] = node_off;
+        append_nodes(h_nodes, bvh, node_off, tri_off);
+        for (uint32_t f : bvh.prim_order) {
+            const float* a = m.vertices + 3 * (size_t)m.indices[3 * (size_t)f];
+            const float* b = m.vertices + 3 * (size_t)m.indices[3 * (size_t)f + 1];
+            const float* c = m.vertices + 3 * (size_t)m.indices[3 * (size_t)f + 2];
+            float fb; memcpy(&fb, &f, 4);
+            h_tris.push_back(make_float4(a[0], a[1], a[2], fb));
+            h_tris.push_back(make_float4(b[0], b[1], b[2], 0.f));
+            h_tris.push_back(make_float4(c[0], c[1], c[2], 0.f));
+        }
+    }
+    sc->n_blas_nodes = (uint32_t)(h_nodes.size() / 5); sc->n_tris = (uint32_t)(h_tris.size() / 3);
+
+    // ---- items ----
+    sc->h_items.resize(d->n_items);
+    for (uint32_t i = 0; i < d->n_items; i++) {
+        DItem& di = sc->h_items[i]; const RtxItem& s = d->items[i];
+        fill_item(*sc, s, di);
+        if (s.shape == RTX_SHAPE_MESH) {
+            const RtxMesh& m = d->meshes[s.mesh]; const MeshOff& o = moff[s.mesh];
+            di.lo = make_float4(o.lo[0], o.lo[1], o.lo[2], 0.f); di.hi.x = o.hi[0]; di.hi.y = o.hi[1]; di.hi.z = o.hi[2];
+            di.root = sc->mesh_root[s.mesh];
+            di.n_faces = m.n_faces; di.n_uv_faces = m.n_uv_faces; di.n_normal_faces = m.n_normal_faces;
+            di.vert_off = o.vert; di.idx_off = o.idx; di.uv_off = o.uv; di.uvidx_off = o.uvidx; di.nrm_off = o.nrm; di.nidx_off = o.nidx;
+            if (m.n_normals > 0 && m.n_normal_faces > 0) di.flags |= IF_HAS_NORMALS;
+        } else {
+            const float r = s.radius;                                     // Ball::aabb
+            di.lo.x = -r; di.lo.y = -r; di.lo.z = -r; di.hi.x = r; di.hi.y = r; di.hi.z = r;
+        }
+    }
+
+    // ---- TLAS (only used above kLinearItems; space reserved for updates) ----
+    std::vector<float4> tlas_nodes; std::vector<uint32_t> tlas_prims;
+    sc->tlas_cap = std::max<uint32_t>(8, d->n_items);
+    if (d->n_items > kLinearItems) { int rc = build_tlas(*sc, tlas_nodes, tlas_prims); if (rc) { rtx_scene_destroy(sc); return rc; } }
+    h_nodes.insert(h_nodes.end(), tlas_nodes.begin(), tlas_nodes.end());
+    h_nodes.resize(((size_t)sc->n_blas_nodes + sc->tlas_cap) * 5, make_float4(0, 0, 0, 0));
+    tlas_prims.resize(std::max<size_t>(1, d->n_items), 0);
+
+    // ---- materials / textures / lights ----
+    std::vector<DTex> h_texs(d->n_textures); std::vector<uchar4> h_texels;
+    for (uint32_t i = 0; i < d->n_textures; i++) {
+        const RtxTexture& t = d->textures[i];
+        size_t off = h_texels.size(), n = (size_t)t.width * t.height;
+        h_texs[i] = DTex{(uint32_t)(off & 0xffffffffu), (uint32_t)(off >> 32), t.width, t.height};
+        if (n && !t.rgba) return bail(RTX_E_INVALID, "texture without pixels");
+        h_texels.resize(off + n);
+        if (n) memcpy(h_texels.data() + off, t.rgba, n * 4);
+    }
+    sc->texture_bytes = h_texels.size() * 4;
+    std::vector<DMaterial> h_mats(d->n_materials);
+    for (uint32_t i = 0; i < d->n_materials; i++) {
+        const RtxMaterial& m = d->materials[i]; DMaterial& o = h_mats[i]; memset(&o, 0, sizeof(o));
+        memcpy(o.ambient, m.ambient_color, 12); memcpy(o.base, m.base_color, 12); memcpy(o.specular, m.specular_color, 12);
+        o.alpha = m.alpha; o.shininess = m.shininess; o.reflectivity = m.reflectivity; o.refraction_index = m.refraction_index;
+        o.normal_map_strength = m.normal_map_strength; o.shadow_softness = m.shadow_softness; o.roughness = m.roughness;
+        o.nearest = m.texture_filtering_nearest; o.receive_shadow = m.receive_shadow; o.monte_carlo = m.monte_carlo;
+        for (int t = 0; t < 8; t++) {
+            o.tex[t] = (m.texture[t] >= 0 && d->textures[m.texture[t]].width > 0) ? m.texture[t] : -1;
+            if (o.tex[t] >= 0) o.any_texture = 1;
+        }
+    }
+    std::vector<DLight> h_lights; fill_lights(d->lights, d->n_lights, h_lights);
+
+    // ---- upload ----
+    int rc;
+    if ((rc = sc->nodes.upload(h_nodes)) || (rc = sc->tris.upload(h_tris)) || (rc = sc->items.upload(sc->h_items)) ||
+        (rc = sc->tlas_prims.upload(tlas_prims)) || (rc = sc->verts.upload(h_verts)) || (rc = sc->idx.upload(h_idx)) ||
+        (rc = sc->uvs.upload(h_uvs)) || (rc = sc->uv_idx.upload(h_uvidx)) || (rc = sc->nrms.upload(h_nrms)) || (rc = sc->n_idx.upload(h_nidx)) ||
+        (rc = sc->mats.upload(h_mats)) || (rc = sc->texs.upload(h_texs)) || (rc = sc->texels.upload(h_texels)) || (rc = sc->lights.upload(h_lights))) {
+        std::string keep = g_err; rtx_scene_destroy(sc); g_err = keep; return rc;
+    }
+    CU(cudaDeviceSynchronize());
+    refresh_dev(*sc);
+    sc->dev.n_lights = d->n_lights;
+    sc->build_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    *out = sc;
+    return RTX_OK;
+}
+
+int rtx_scene_destroy(RtxScene* sc) {
+    if (!sc) return RTX_OK;
+    cudaSetDevice(sc->device);
+    cudaDeviceSynchronize();
+    sc->nodes.release(); sc->tris.release(); sc->items.release(); sc->tlas_prims.release();
+    sc->verts.release(); sc->uvs.release(); sc->nrms.release(); sc->idx.release(); sc->uv_idx.release(); sc->n_idx.release();
+    sc->mats.release(); sc->texs.release(); sc->texels.release(); sc->lights.release();
+    sc->accum_c.release(); sc->accum_n.release(); sc->ids.release(); sc->sample_table.release();
+    sc->q_o.release(); sc->q_d.release(); sc->q_m.release(); sc->s_o.release(); sc->s_d.release(); sc->s_c.release(); sc->s_r.release();
+    sc->hits.release(); sc->ctr_pool.release(); sc->overflow.release(); sc->counters.release();
+    sc->o_rgba.release(); sc->o_normals.release(); sc->o_depth.release(); sc->o_ids.release(); sc->p_rays.release(); sc->p_hits.release();
+    for (auto& kv : sc->pixel_lists) { kv.second->d.release(); delete kv.second; }
+    for (cudaEvent_t e : sc->events) cudaEventDestroy(e);
+    if (sc->h_ctr) cudaFreeHost(sc->h_ctr);
+    delete sc;
+    return RTX_OK;
+}
+
+int rtx_scene_update_items(RtxScene* sc, const RtxItemXform* x, size_t n) {
+    if (!sc || (!x && n)) return fail(RTX_E_INVALID, "null argument");
+    CU(cudaSetDevice(sc->device));
+    for (size_t i = 0; i < n; i++) {
+        if (x[i].item_index >= sc->src_items.size()) return fail(RTX_E_INVALID, "item index out of range");
+        const float* ti = x[i].tran_inverse;
+        if (ti[3] != 0.0f || ti[7] != 0.0f || ti[11] != 0.0f || ti[15] != 1.0f) return fail(RTX_E_NON_AFFINE, "item transform is not affine");
+    }
+    for (size_t i = 0; i < n; i++) {
+        RtxItem& s = sc->src_items[x[i].item_index]; DItem& d = sc->h_items[x[i].item_index];
+        memcpy(s.trans, x[i].trans, 64); memcpy(s.tran_inverse, x[i].tran_inverse, 64);
+        for (int r = 0; r < 3; r++) {
+            d.inv[r] = make_float4(s.tran_inverse[0 + r], s.tran_inverse[4 + r], s.tran_inverse[8 + r], s.tran_inverse[12 + r]);
+            d.mat[r] = make_float4(s.trans[0 + r], s.trans[4 + r], s.trans[8 + r], s.trans[12 + r]);
+        }
+    }
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(sc->items.p, sc->h_items.data(), sc->h_items.size() * sizeof(DItem), cudaMemcpyHostToDevice));
+    if (sc->h_items.size() > kLinearItems) {                              // Scene::update rebuilds the item BVH (scene.rs:1681-1687)
+        std::vector<float4> tn; std::vector<uint32_t> tp;
+        int rc = build_tlas(*sc, tn, tp); if (rc) return rc;
+        if (tn.size() / 5 > sc->tlas_cap) return fail(RTX_E_INVALID, "TLAS capacity exceeded");
+        CU(cudaMemcpy(sc->nodes.p + (size_t)sc->n_blas_nodes * 5, tn.data(), tn.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(sc->tlas_prims.p, tp.data(), tp.size() * 4, cudaMemcpyHostToDevice));
+    }
+    return RTX_OK;
+}
+
+int rtx_scene_set_lights(RtxScene* sc, const RtxLight* l, uint32_t n) {
+    if (!sc || (!l && n)) return fail(RTX_E_INVALID, "null argument");
+    CU(cudaSetDevice(sc->device));
+    std::vector<DLight> h; fill_lights(l, n, h);
+    CU(cudaDeviceSynchronize());
+    int rc = sc->lights.upload(h); if (rc) return rc;
+    CU(cudaDeviceSynchronize());
+    refresh_dev(*sc);
+    sc->dev.n_lights = n;
+    return RTX_OK;
+}
+
+int rtx_scene_bvh_info(const RtxScene* sc, RtxBvhInfo* info) {
+    if (!sc || !info) return fail(RTX_E_INVALID, "null argument");
+    info->n_nodes = sc->n_blas_nodes; info->n_triangles = sc->n_tris; info->n_items = (uint32_t)sc->h_items.size();
+    info->tlas_nodes = sc->n_tlas_nodes; info->node_bytes = (uint64_t)(sc->n_blas_nodes + sc->n_tlas_nodes) * 80;
+    info->triangle_bytes = (uint64_t)sc->n_tris * 48; info->item_bytes = sc->h_items.size() * sizeof(DItem);
+    info->texture_bytes = sc->texture_bytes; info->build_ms = sc->build_ms;
+    return RTX_OK;
+}
+
+// ---- the frame ------------------------------------------------------------------------------------
+int rtx_render_frame_device(RtxScene* sc, const RtxCamera* cam, const RtxConfig* cfg, const RtxShard* shard, void* d_rgba, void* d_normals,
+                            void* d_depth, void* d_object_ids, void* cuda_stream, RtxStats* stats) {
+    if (!sc || !cam || !cfg) return fail(RTX_E_INVALID, "null argument");
+    if (cam->width == 0 || cam->height == 0 || (uint64_t)cam->width * cam->height > 0x7fffffffull) return fail(RTX_E_INVALID, "bad frame size");
+    if (cfg->samples == 0 || cfg->samples > 65535) return fail(RTX_E_INVALID, "samples out of range (u16)");
+    if (cfg->max_recursion > 254) return fail(RTX_E_INVALID, "max_recursion > 254 is not supported");
+    CU(cudaSetDevice(sc->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const bool want_stats = cfg->debug_flags & RTX_DEBUG_COLLECT_STATS, ordered = cfg->debug_flags & RTX_DEBUG_ORDERED_SHADOW;
+    int rc;
+    PixelList* pl;
+    if ((rc = get_pixel_list(*sc, cam->width, cam->height, shard, &pl))) return rc;
+    if ((rc = ensure_frame(*sc, cam->width, cam->height))) return rc;
+    uint32_t n_enabled = 0;
+    {
+        // enabled lights are counted on the host copy of the device lights
+        std::vector<DLight> hl(sc->dev.n_lights);
+        if (!hl.empty()) CU(cudaMemcpy(hl.data(), sc->lights.p, hl.size() * sizeof(DLight), cudaMemcpyDeviceToHost));
+        for (auto& l : hl) if (l.enabled) n_enabled++;
+    }
+    if ((rc = ensure_queues(*sc, cfg->max_recursion, n_enabled))) return rc;
+    if ((rc = occupancy_blocks(*sc))) return rc;
+    uint64_t h2d = 0;
+    if (sc->table_samples != cfg->samples) {
+        std::vector<ushort2> t; make_sample_table(cfg->samples, sc->cell_size, t);
+        if ((rc = sc->sample_table.upload(t, st))) return rc;
+        sc->table_samples = cfg->samples; h2d += t.size() * 4;
+    }
+    FrameDev F; memset(&F, 0, sizeof(F));
+    memcpy(F.pinv, cam->projection_inverse, 64); memcpy(F.vinv, cam->view_inverse, 64);
+    F.width = cam->width; F.height = cam->height; F.n_samples = cfg->samples; F.cell_size = sc->cell_size;
+    F.monte_carlo = cfg->monte_carlo; F.max_recursion = cfg->max_recursion; F.gamma = cfg->gamma_correction; F.mc_seed = cfg->mc_seed;
+    F.focal_length = cfg->focal_length; F.aperture_size = cfg->aperture_size; F.fog_density = cfg->fog_density;
+    memcpy(F.fog_color, cfg->fog_color, 12); F.debug_flags = cfg->debug_flags;
+    F.sample_table = sc->sample_table.p; F.accum_c = sc->accum_c.p; F.accum_n = sc->accum_n.p; F.ids = sc->ids.p;
+    h2d += sizeof(FrameDev);                                             // kernel parameters (camera + config)
+
+    // events: [0] frame start, [1] frame end, then 4 per wave (closest start/end, shadow start/end)
+    auto get_event = [&](size_t i) -> cudaEvent_t {
+        while (sc->events.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); sc->events.push_back(e); }
+        return sc->events[i];
+    };
+    size_t ev_next = 2;
+    float trace_ms = 0.f;
+    CU(cudaEventRecord(get_event(0), st));
+    CU(cudaMemsetAsync(sc->ctr_pool.p, 0, kCtrPool * 4, st));
+    CU(cudaMemsetAsync(sc->overflow.p, 0, 4, st));
+    if (want_stats) CU(cudaMemsetAsync(sc->counters.p, 0, sizeof(Counters), st));
+    uint64_t launches = 0;
+    const int gs = sc->sm_count * 8;
+    clear_pixels_kernel<<<gs, 256, 0, st>>>(F, pl->d.p, pl->n); launches++;
+
+    const uint32_t L = cfg->max_recursion + 1;                           // deepest ray depth
+    std::vector<uint32_t> counts(L + 2, 0);
+    const uint32_t chunk = sc->chunk;
+    // primary batches: pixel ranges of <= chunk pixels x sample ranges so that np*ns <= chunk
+    const uint32_t np_full = std::min(pl->n, chunk);
+    const uint32_t ns_full = std::max(1u, chunk / std::max(1u, np_full));
+    uint32_t cur_p0 = 0, cur_s0 = 0;
+    bool primary_left = pl->n > 0;
+    uint32_t ctr_idx = 0, waves = 0, batches = 0;
+    uint64_t rays_closest = 0, rays_shadow = 0, primary = 0;
+    ShadowQ SQ{sc->s_o.p, sc->s_d.p, sc->s_c.p, sc->s_r.p};
+
+    for (;;) {
+        int level = -1;
+        for (int d = (int)L; d >= 1; d--) if (counts[d] >= chunk) { level = d; break; }
+        if (level < 0 && primary_left) level = 0;
+        if (level < 0) for (uint32_t d = 1; d <= L; d++) if (counts[d] > 0) { level = (int)d; break; }
+        if (level < 0) break;
+        if (level == 0) {
+            const uint32_t np = std::min(np_full, pl->n - cur_p0), ns = std::min(ns_full, cfg->samples - cur_s0);
+            const uint32_t n = np * ns;
+            raygen_kernel<<<std::min<uint32_t>((n + 255) / 256, gs), 256, 0, st>>>(F, pl->d.p, cur_p0, np, cur_s0, ns, level_queue(*sc, 1), counts[1]);
+            launches++; batches++;
+            counts[1] += n; primary += n;
+            cur_s0 += ns;
+            if (cur_s0 >= cfg->samples) { cur_s0 = 0; cur_p0 += np; if (cur_p0 >= pl->n) primary_left = false; }
+            continue;
+        }
+        // ---- one wave at depth `level` ----
+        const uint32_t d = (uint32_t)level;
+        const uint32_t n = std::min(counts[d], chunk);
+        const uint32_t q_base = counts[d] - n;
+        counts[d] -= n;
+        if (ctr_idx + 4 > kCtrPool) {                                    // stream is idle here (we sync every wave)
+            CU(cudaMemsetAsync(sc->ctr_pool.p, 0, kCtrPool * 4, st)); ctr_idx = 0;
+        }
+        uint32_t* ctr = sc->ctr_pool.p + ctr_idx; ctr_idx += 4;          // [0] closest work, [1] shadow work, [2] child count, [3] shadow count
+        RayQ Q = level_queue(*sc, d);
+        const uint32_t warps = (n + 31) / 32;
+        cudaEvent_t e0 = get_event(ev_next), e1 = get_event(ev_next + 1), e2 = get_event(ev_next + 2), e3 = get_event(ev_next + 3);
+        ev_next += 4;
+        CU(cudaEventRecord(e0, st));
+        {
+            const int maxb = want_stats ? sc->blocks_closest_st : sc->blocks_closest;
+            const int blocks = (int)std::min<uint32_t>((warps + (kTraceBlock / 32) - 1) / (kTraceBlock / 32), (uint32_t)maxb);
+            if (want_stats) closest_kernel<true><<<blocks, kTraceBlock, 0, st>>>(sc->dev, Q, q_base, n, sc->hits.p, ctr, sc->counters.p);
+            else closest_kernel<false><<<blocks, kTraceBlock, 0, st>>>(sc->dev, Q, q_base, n, sc->hits.p, ctr, sc->counters.p);
+            launches++;
+        }
+        CU(cudaEventRecord(e1, st));
+        {
+            ShadeOut so;
+            const uint32_t nd = d + 1 <= L ? d + 1 : d;                  // depth L never spawns children (depth <= max_recursion fails)
+            RayQ C = level_queue(*sc, nd);
+            const uint32_t off = d + 1 <= L ? counts[d + 1] : 0;
+            so.child = RayQ{C.o + off, C.d + off, C.m + off};
+            so.child_cap = d + 1 <= L ? sc->level_cap - off : 0;
+            so.child_count = ctr + 2;
+            so.shadow = SQ; so.shadow_cap = sc->shadow_cap; so.shadow_count = ctr + 3; so.overflow = sc->overflow.p;
+            const int blocks = (int)std::min<uint32_t>((n + kShadeBlock - 1) / kShadeBlock, (uint32_t)sc->sm_count * 16);
+            shade_kernel<<<blocks, kShadeBlock, 0, st>>>(sc->dev, F, Q, q_base, n, sc->hits.p, so);
+            launches++;
+        }
+        CU(cudaEventRecord(e2, st));
+        if (n_enabled > 0) {
+            if (ordered) shadow_kernel<false, true><<<sc->blocks_shadow_ord, kTraceBlock, 0, st>>>(sc->dev, F, SQ, ctr + 3, d, ctr + 1, sc->counters.p);
+            else if (want_stats) shadow_kernel<true, false><<<sc->blocks_shadow_st, kTraceBlock, 0, st>>>(sc->dev, F, SQ, ctr + 3, d, ctr + 1, sc->counters.p);
+            else shadow_kernel<false, false><<<sc->blocks_shadow, kTraceBlock, 0, st>>>(sc->dev, F, SQ, ctr + 3, d, ctr + 1, sc->counters.p);
+            launches++;
+        }
+        CU(cudaEventRecord(e3, st));
+        CU(cudaMemcpyAsync(sc->h_ctr, ctr, 16, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (d + 1 <= L) counts[d + 1] += sc->h_ctr[2];
+        rays_closest += n; rays_shadow += sc->h_ctr[3];
+        waves++;
+        if (d + 1 <= L && counts[d + 1] > sc->level_cap) return fail(RTX_E_INVALID, "internal: ray queue overflow");
+        if (sc->h_ctr[3] > sc->shadow_cap) return fail(RTX_E_INVALID, "internal: shadow queue overflow");
+    }
+    resolve_kernel<<<std::min<uint32_t>((pl->n + 255) / 256, gs), 256, 0, st>>>(F, pl->d.p, pl->n, (uchar4*)d_rgba, (float*)d_normals, (float*)d_depth,
+                                                                            (uint32_t*)d_object_ids);
+    launches++;
+    CU(cudaEventRecord(get_event(1), st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        float ms = 0.f; cudaEventElapsedTime(&ms, sc->events[0], sc->events[1]);
+        float tc = 0.f, ts = 0.f;
+        for (size_t i = 2; i + 3 < ev_next + 0 && i + 3 < sc->events.size(); i += 4) {
+            float a = 0.f, b = 0.f;
+            cudaEventElapsedTime(&a, sc->events[i], sc->events[i + 1]); cudaEventElapsedTime(&b, sc->events[i + 2], sc->events[i + 3]);
+            tc += a; ts += b;
+        }
+        trace_ms = tc + ts;
+        stats->device_ms = ms; stats->trace_ms = trace_ms; stats->shade_ms = ms - trace_ms;
+        stats->rays_closest = rays_closest; stats->rays_shadow = rays_shadow; stats->primary_samples = primary;
+        stats->kernel_launches = launches; stats->waves = waves; stats->batches = batches;
+        stats->h2d_bytes = h2d; stats->d2h_bytes = (uint64_t)waves * 16;
+        if (want_stats) {
+            Counters c; CU(cudaMemcpy(&c, sc->counters.p, sizeof(c), cudaMemcpyDeviceToHost));
+            stats->node_visits = c.node_visits; stats->tri_tests = c.tri_tests; stats->sphere_tests = c.sphere_tests; stats->item_tests = c.item_tests;
+        }
+        // closest / shadow split of trace_ms is exposed through the two reserved-for-later fields of the stats struct:
+        // trace_ms = closest + shadow; shade_ms = everything else on the device.
+        (void)tc; (void)ts;
+    }
+    return RTX_OK;
+}
+
+int rtx_render_frame(RtxScene* sc, const RtxCamera* cam, const RtxConfig* cfg, uint8_t* rgba, float* normals, float* depth, uint32_t* object_ids,
+                     RtxStats* stats) {
+    if (!sc || !cam || !cfg) return fail(RTX_E_INVALID, "null argument");
+    CU(cudaSetDevice(sc->device));
+    const size_t n = (size_t)cam->width * cam->height;
+    int rc;
+    if ((rc = sc->o_rgba.alloc(n)) || (rc = sc->o_normals.alloc(3 * n)) || (rc = sc->o_depth.alloc(n)) || (rc = sc->o_ids.alloc(n))) return rc;
+    RtxStats st;
+    rc = rtx_render_frame_device(sc, cam, cfg, nullptr, sc->o_rgba.p, sc->o_normals.p, sc->o_depth.p, sc->o_ids.p, nullptr, &st);
+    if (rc) return rc;
+    if (rgba) { CU(cudaMemcpy(rgba, sc->o_rgba.p, n * 4, cudaMemcpyDeviceToHost)); st.d2h_bytes += n * 4; }
+    if (normals) { CU(cudaMemcpy(normals, sc->o_normals.p, n * 12, cudaMemcpyDeviceToHost)); st.d2h_bytes += n * 12; }
+    if (depth) { CU(cudaMemcpy(depth, sc->o_depth.p, n * 4, cudaMemcpyDeviceToHost)); st.d2h_bytes += n * 4; }
+    if (object_ids) { CU(cudaMemcpy(object_ids, sc->o_ids.p, n * 4, cudaMemcpyDeviceToHost)); st.d2h_bytes += n * 4; }
+    if (stats) *stats = st;
+    return RTX_OK;
+}
+
+// ---- probe ------------------------------------------------------------------------------------------
+int rtx_trace_probe(RtxScene* sc, const RtxRay* rays, size_t n, int for_shadow, int stop_on_first_hit, uint32_t depth, RtxHit* hits) {
+    if (!sc || (n && (!rays || !hits))) return fail(RTX_E_INVALID, "null argument");
+    if (n == 0) return RTX_OK;
+    if (n > 0x7fffffffull) return fail(RTX_E_INVALID, "too many rays");
+    static_assert(sizeof(ProbeRay) == sizeof(RtxRay) && sizeof(ProbeHit) == sizeof(RtxHit), "probe layouts");
+    CU(cudaSetDevice(sc->device));
+    int rc;
+    if ((rc = sc->p_rays.alloc(n)) || (rc = sc->p_hits.alloc(n))) return rc;
+    CU(cudaMemcpy(sc->p_rays.p, rays, n * sizeof(RtxRay), cudaMemcpyHostToDevice));
+    probe_kernel<<<(unsigned)((n + 127) / 128), 128>>>(sc->dev, sc->p_rays.p, (uint32_t)n, for_shadow, stop_on_first_hit, depth, sc->p_hits.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(hits, sc->p_hits.p, n * sizeof(RtxHit), cudaMemcpyDeviceToHost));
+    return RTX_OK;
+}
+
+// ---- shards -------------------------------------------------------------------------------------------
+uint64_t rtx_shard_pixel_count(uint32_t w, uint32_t h, const RtxShard* shard) {
+    RtxShard sh = shard ? *shard : RtxShard{0, 1, 8, 4};
+    if (sh.world == 0 || sh.rank >= sh.world || sh.tile_w == 0 || sh.tile_h == 0) return 0;
+    const uint32_t tx = (w + sh.tile_w - 1) / sh.tile_w, ty = (h + sh.tile_h - 1) / sh.tile_h;
+    uint64_t n = 0;
+    for (uint32_t t = sh.rank; t < tx * ty; t += sh.world) {
+        const uint32_t x0 = (t % tx) * sh.tile_w, y0 = (t / tx) * sh.tile_h;
+        n += (uint64_t)(std::min(x0 + sh.tile_w, w) - x0) * (std::min(y0 + sh.tile_h, h) - y0);
+    }
+    return n;
+}
+uint64_t rtx_shard_packed_bytes(uint32_t w, uint32_t h, const RtxShard* shard) { return rtx_shard_pixel_count(w, h, shard) * 24; }
+
+static int shard_list(uint32_t w, uint32_t h, const RtxShard* shard, cudaStream_t st, uint32_t** d_list, uint32_t* n) {
+    // pack/unpack are scene-independent: keep one small cache of device pixel lists per process
+    static std::map<std::tuple<int, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t>, std::pair<uint32_t*, uint32_t>> cache;
+    RtxShard sh = shard ? *shard : RtxShard{0, 1, 8, 4};
+    if (sh.world == 0 || sh.rank >= sh.world || sh.tile_w == 0 || sh.tile_h == 0) return fail(RTX_E_INVALID, "bad shard");
+    int dev = 0; CU(cudaGetDevice(&dev));
+    auto key = std::make_tuple(dev, w, h, sh.rank, sh.world, sh.tile_w, sh.tile_h);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        std::vector<uint32_t> px;
+        const uint32_t tx = (w + sh.tile_w - 1) / sh.tile_w, ty = (h + sh.tile_h - 1) / sh.tile_h;
+        for (uint32_t t = sh.rank; t < tx * ty; t += sh.world) {
+            const uint32_t x0 = (t % tx) * sh.tile_w, y0 = (t / tx) * sh.tile_h;
+            for (uint32_t y = y0; y < std::min(y0 + sh.tile_h, h); y++)
+                for (uint32_t x = x0; x < std::min(x0 + sh.tile_w, w); x++) px.push_back(y * w + x);
+        }
+        uint32_t* p = nullptr;
+        CU(cudaMalloc(&p, std::max<size_t>(1, px.size()) * 4));
+        if (!px.empty()) CU(cudaMemcpy(p, px.data(), px.size() * 4, cudaMemcpyHostToDevice));
+        it = cache.emplace(key, std::make_pair(p, (uint32_t)px.size())).first;
+    }
+    (void)st;
+    *d_list = it->second.first; *n = it->second.second;
+    return RTX_OK;
+}
+
+int rtx_shard_pack(uint32_t w, uint32_t h, const RtxShard* shard, const void* d_rgba, const void* d_normals, const void* d_depth,
+                   const void* d_ids, void* d_packed, void* cuda_stream) {
+    if (!d_rgba || !d_normals || !d_depth || !d_ids || !d_packed) return fail(RTX_E_INVALID, "null argument");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    uint32_t* list; uint32_t n; int rc = shard_list(w, h, shard, st, &list, &n); if (rc) return rc;
+    if (n == 0) return RTX_OK;
+    uint8_t* base = (uint8_t*)d_packed;
+    pack_kernel<<<std::min<uint32_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(list, n, (const uchar4*)d_rgba, (const float*)d_normals, (const float*)d_depth,
+                                                                          (const uint32_t*)d_ids, (uchar4*)base, (float*)(base + (size_t)n * 4),
+                                                                          (float*)(base + (size_t)n * 16), (uint32_t*)(base + (size_t)n * 20));
+    CU(cudaGetLastError());
+    return RTX_OK;
+}
+
+int rtx_shard_unpack(uint32_t w, uint32_t h, const RtxShard* shard, const void* d_packed, void* d_rgba, void* d_normals, void* d_depth,
+                     void* d_ids, void* cuda_stream) {
+    if (!d_rgba || !d_normals || !d_depth || !d_ids || !d_packed) return fail(RTX_E_INVALID, "null argument");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    uint32_t* list; uint32_t n; int rc = shard_list(w, h, shard, st, &list, &n); if (rc) return rc;
+    if (n == 0) return RTX_OK;
+    const uint8_t* base = (const uint8_t*)d_packed;
+    unpack_kernel<<<std::min<uint32_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(list, n, (const uchar4*)base, (const float*)(base + (size_t)n * 4),
+                                                                            (const float*)(base + (size_t)n * 16), (const uint32_t*)(base + (size_t)n * 20),
+                                                                            (uchar4*)d_rgba, (float*)d_normals, (float*)d_depth, (uint32_t*)d_ids);
+    CU(cudaGetLastError());
+    return RTX_OK;
+}
+
+// ---- post-processing (reference src/post_processing.rs:77-181) ---------------------------------------
+__global__ void post_kernel(uint32_t w, uint32_t h, int cavity, int outline, uchar4* rgba, const float* normals, const uint32_t* ids) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t total = w * h;
+    if (i >= total) return;
+    const int x = (int)(i % w), y = (int)(i / w), wi = (int)w;
+    uchar4 px = rgba[i];
+    float r = (float)px.x, g = (float)px.y, b = (float)px.z;
+    auto id_at = [&](int ox, int oy) -> uint32_t { const long idx = (long)(y + oy) * wi + (x + ox); return (idx < 0 || idx >= (long)total) ? 0u : ids[idx]; };
+    auto n_at = [&](int ox, int oy, int comp) -> float { const long idx = (long)(y + oy) * wi + (x + ox); return (idx < 0 || idx >= (long)total) ? 0.0f : normals[3 * idx + comp]; };
+    if (outline) {                                                        // calculate_outline :96-121
+        const uint32_t c = id_at(0, 0);
+        const float eq = ((id_at(0, 1) == c ? 0.25f : 0.0f) + (id_at(0, -1) == c ? 0.25f : 0.0f)) + ((id_at(-1, 0) == c ? 0.25f : 0.0f) + (id_at(1, 0) == c ? 0.25f : 0.0f));
+        const float o = 1.0f - eq;
+        if (o > 0.0f) { r = o * 255.0f; g = o * 255.0f; b = o * 255.0f; }
+    }
+    if (cavity) {                                                         // calculate_curvature :77-94 (.xz() of the normal: .y of that is z)
+        const float diff = (n_at(0, 1, 2) - n_at(0, -1, 2)) + (n_at(1, 0, 0) - n_at(-1, 0, 0));
+        auto soft = [](float c, float control) { return (c < 0.5f / control) ? c * (1.0f - c * control) : 0.25f / control; };
+        const float curv = diff < 0.0f ? -2.0f * soft(-diff, 1.0f) : 2.0f * soft(diff, 1.15f);
+        r *= curv + 1.0f; g *= curv + 1.0f; b *= curv + 1.0f;
+    }
+    // f32::clamp keeps NaN; `as u8` maps NaN to 0
+    auto cl = [](float v) { return v != v ? v : fminf(fmaxf(v, 0.0f), 255.0f); };
+    rgba[i] = make_uchar4((unsigned char)as_u8(cl(r)), (unsigned char)as_u8(cl(g)), (unsigned char)as_u8(cl(b)), 255);
+}
+
+int rtx_post_process_device(uint32_t w, uint32_t h, int cavity, int outline, void* d_rgba, const void* d_normals, const void* d_depth,
+                            const void* d_ids, void* cuda_stream) {
+    (void)d_depth;
+    if (!d_rgba || !d_normals || !d_ids) return fail(RTX_E_INVALID, "null argument");
+    const uint32_t n = w * h;
+    if (n == 0) return RTX_OK;
+    post_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)cuda_stream>>>(w, h, cavity, outline, (uchar4*)d_rgba, (const float*)d_normals, (const uint32_t*)d_ids);
+    CU(cudaGetLastError());
+    return RTX_OK;
+}
+
+}  // extern "C"

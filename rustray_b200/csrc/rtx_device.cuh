@@ -1,0 +1,712 @@
+// rtx_device.cuh — device-side data layout and math of the B200 ray-casting path.
+//
+// Data layout in HBM (all 16-byte aligned, read with 128-bit loads):
+//   nodes   : 80-byte wide BVH nodes (5 x float4), all per-mesh BLASes + the item TLAS concatenated
+//   tris    : 48 bytes per triangle (3 x float4: a|face, b|-, c|-) in BVH leaf order, object space
+//   items   : DItem (M^-1 rows, M rows, local AABB, flags, offsets)
+//   mesh arrays (verts / indices / uvs / uv indices / normals / normal indices) for shading only
+//   materials, texture table + RGBA8 texel pool, lights
+//
+// Arithmetic that decides a hit (ray -> object space, AABB slab key, ball and triangle tests) uses
+// __fmul_rn/__fadd_rn/... so that nvcc cannot contract it into FMAs: the reference is Rust (never
+// contracted), and the CPU oracle is built with -ffp-contract=off, so hit distances are bit-equal.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rtx {
+
+// ------------------------------------------------------------------------------------------------
+// layout
+// ------------------------------------------------------------------------------------------------
+enum : uint32_t {
+    IF_MESH = 1u, IF_VISIBLE = 2u, IF_FLIP = 4u, IF_CAST_SHADOW = 8u, IF_REFL_ONLY = 16u, IF_BACKFACE = 32u,
+    IF_SMOOTH = 64u, IF_HAS_NORMALS = 128u, IF_ALPHA_TEX = 256u, IF_ALPHA_POS = 512u, IF_ALPHA_LT1 = 1024u
+};
+
+struct alignas(16) DItem {
+    float4 inv[3];      // rows 0..2 of tran_inverse (affine)
+    float4 mat[3];      // rows 0..2 of trans
+    float4 lo;          // local AABB min, w = radius
+    float4 hi;          // local AABB max, w = cached material alpha
+    uint32_t flags, id, material, root;               // root = BLAS root node (mesh)
+    uint32_t n_faces, n_uv_faces, n_normal_faces, pad0;
+    uint32_t vert_off, idx_off, uv_off, uvidx_off;    // element offsets into the mesh arrays
+    uint32_t nrm_off, nidx_off, pad1, pad2;
+};
+
+struct alignas(16) DMaterial {
+    float ambient[3]; float alpha;
+    float base[3]; float shininess;
+    float specular[3]; float reflectivity;
+    float refraction_index, normal_map_strength, shadow_softness, roughness;
+    int32_t tex[8];
+    uint32_t nearest, receive_shadow, monte_carlo, any_texture;
+};
+
+struct DTex { uint32_t offset_lo, offset_hi, w, h; };     // texel offset (64-bit) into the pool
+struct alignas(16) DLight { float pos[3]; uint32_t type; float dir[3]; float intensity; float color[3]; float max_angle; uint32_t enabled, pad[3]; };
+
+struct SceneDev {
+    const float4* nodes; const float4* tris; const DItem* items;
+    const uint32_t* tlas_prims;
+    const float* verts; const uint32_t* idx; const float* uvs; const uint32_t* uv_idx; const float* nrms; const uint32_t* n_idx;
+    const DMaterial* mats; const DTex* texs; const uchar4* texels; const DLight* lights;
+    uint32_t n_items, n_lights, tlas_root, use_tlas;
+    uint32_t ball_flip_inside, pad[3];
+};
+
+struct FrameDev {
+    float pinv[16], vinv[16];
+    uint32_t width, height, n_samples, cell_size;
+    uint32_t monte_carlo, max_recursion, gamma, mc_seed;
+    float focal_length, aperture_size, fog_density, pad0;
+    float fog_color[3]; uint32_t debug_flags;
+    const ushort2* sample_table;
+    float4* accum_c;      // per frame pixel: rgb sum, depth sum
+    float4* accum_n;      // per frame pixel: normal sum
+    uint32_t* ids;        // per frame pixel: object id of the last sample
+};
+
+// ray queue (SoA): o.xyz + weight | d.xyz + pixel | meta (sample:16 depth:8 flags:8, path)
+struct RayQ { float4* o; float4* d; uint2* m; };
+// shadow queue (SoA): o.xyz + light distance | d.xyz + pixel | contribution rgb + receiver alpha | receiver item
+struct ShadowQ { float4* o; float4* d; float4* c; uint32_t* r; };
+struct alignas(16) HitRec { float t; uint32_t item; uint32_t prim; uint32_t flags; };   // item = ~0u: miss
+enum : uint32_t { HF_BACK = 1u, HF_INSIDE = 2u, HF_NEGN = 4u };   // HF_NEGN: parry returned -normalize(n) (t < 0 branch)
+enum : uint32_t { RF_ID_OWNER = 1u };
+
+struct Counters {      // device counters, 64-bit
+    unsigned long long rays_closest, rays_shadow, node_visits, tri_tests, sphere_tests, item_tests;
+};
+
+// ------------------------------------------------------------------------------------------------
+// exact (never contracted) f32 helpers — mirror nalgebra's evaluation order
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float xm(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float xa(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float xs(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float xd(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float xsqrt(float a) { return __fsqrt_rn(a); }
+__device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+__device__ __forceinline__ float3 xsub(float3 a, float3 b) { return f3(xs(a.x, b.x), xs(a.y, b.y), xs(a.z, b.z)); }
+__device__ __forceinline__ float3 xadd(float3 a, float3 b) { return f3(xa(a.x, b.x), xa(a.y, b.y), xa(a.z, b.z)); }
+__device__ __forceinline__ float3 xscale(float3 a, float s) { return f3(xm(a.x, s), xm(a.y, s), xm(a.z, s)); }
+__device__ __forceinline__ float3 xneg(float3 a) { return f3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float xdot(float3 a, float3 b) { return xa(xa(xm(a.x, b.x), xm(a.y, b.y)), xm(a.z, b.z)); }
+__device__ __forceinline__ float3 xcross(float3 a, float3 b) {
+    return f3(xs(xm(a.y, b.z), xm(a.z, b.y)), xs(xm(a.z, b.x), xm(a.x, b.z)), xs(xm(a.x, b.y), xm(a.y, b.x)));
+}
+__device__ __forceinline__ float xnorm(float3 a) { return xsqrt(xdot(a, a)); }
+__device__ __forceinline__ float3 xnormalize(float3 a) { float n = xnorm(a); return f3(xd(a.x, n), xd(a.y, n), xd(a.z, n)); }
+// row r of an affine 3x4 (row = m[r][0..3]) times (x,y,z,w): ((m0*x + m1*y) + m2*z) + m3*w
+__device__ __forceinline__ float xrow(float4 r, float3 v, float w) { return xa(xa(xa(xm(r.x, v.x), xm(r.y, v.y)), xm(r.z, v.z)), xm(r.w, w)); }
+__device__ __forceinline__ float3 xform_point(const float4 m[3], float3 p) { return f3(xrow(m[0], p, 1.0f), xrow(m[1], p, 1.0f), xrow(m[2], p, 1.0f)); }
+__device__ __forceinline__ float3 xform_vec(const float4 m[3], float3 v) { return f3(xrow(m[0], v, 0.0f), xrow(m[1], v, 0.0f), xrow(m[2], v, 0.0f)); }
+
+// plain float3 helpers (shading; contraction allowed)
+__device__ __forceinline__ float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 operator-(float3 a) { return f3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float3 operator*(float s, float3 a) { return f3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float dot3(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float3 cross3(float3 a, float3 b) { return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ float len3(float3 a) { return sqrtf(dot3(a, a)); }
+__device__ __forceinline__ float3 norm3(float3 a) { float n = len3(a); return f3(a.x / n, a.y / n, a.z / n); }
+
+// Rust `as` casts: saturating, NaN -> 0
+__device__ __forceinline__ uint32_t as_u32(float f) { return __float2uint_rz(f); }
+__device__ __forceinline__ int32_t as_i32(float f) { return __float2int_rz(f); }
+__device__ __forceinline__ uint32_t as_u8(float f) { uint32_t v = __float2uint_rz(f); return v > 255u ? 255u : v; }
+__device__ __forceinline__ bool approx_equal(float a, float b) { return truncf(xm(a, 1000000.0f)) == truncf(xm(b, 1000000.0f)); }
+
+// counter-based RNG — identical to oracle/rt_oracle.cpp mc_uniform
+__device__ __forceinline__ uint32_t mix32(uint32_t h) { h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16; return h; }
+__device__ __forceinline__ float mc_uniform(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t path, uint32_t slot) {
+    uint32_t h = mix32(seed ^ 0x9E3779B9u);
+    h = mix32(h ^ (pixel * 0x85EBCA6Bu + 0x165667B1u));
+    h = mix32(h ^ (sample * 0xC2B2AE35u + 0x27D4EB2Fu));
+    h = mix32(h ^ (path * 0x9E3779B1u + slot * 0x632BE5ABu + 0x7F4A7C15u));
+    return __fmul_rn((float)(h >> 8), 1.0f / 16777216.0f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// primitive tests (restating parry3d 0.13; see oracle/rt_oracle.cpp for the citations)
+// ------------------------------------------------------------------------------------------------
+// Aabb::cast_local_ray(ray, f32::MAX, solid) — reference call sites src/shape/sphere.rs:51, mesh.rs:58
+__device__ __forceinline__ bool aabb_cast(float3 lo, float3 hi, float3 o, float3 d, bool solid, float& key) {
+    float tmin = 0.0f, tmax = 3.402823466e+38f;
+    const float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z}, mn[3] = {lo.x, lo.y, lo.z}, mx[3] = {hi.x, hi.y, hi.z};
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        if (dd[i] == 0.0f) {
+            if (oo[i] < mn[i] || oo[i] > mx[i]) return false;
+        } else {
+            float denom = xd(1.0f, dd[i]);
+            float n = xm(xs(mn[i], oo[i]), denom), f = xm(xs(mx[i], oo[i]), denom);
+            if (n > f) { float t = n; n = f; f = t; }
+            tmin = fmaxf(tmin, n);
+            tmax = fminf(tmax, f);
+            if (tmin > tmax) return false;
+        }
+    }
+    key = (tmin == 0.0f && !solid) ? tmax : tmin;
+    return true;
+}
+
+// ray_toi_with_ball (center = origin) — reference call site src/shape/sphere.rs:60
+__device__ __forceinline__ bool ball_cast(float radius, float3 o, float3 d, bool solid, float& toi, bool& inside) {
+    float a = xdot(d, d), b = xdot(o, d), c = xs(xdot(o, o), xm(radius, radius));
+    if (a == 0.0f) { if (c > 0.0f) return false; inside = true; toi = 0.0f; return true; }
+    if (c > 0.0f && b > 0.0f) return false;
+    float delta = xs(xm(b, b), xm(a, c));
+    if (delta < 0.0f) return false;
+    float sq = xsqrt(delta);
+    float t = xd(xs(-b, sq), a);
+    if (t <= 0.0f) { inside = true; toi = solid ? 0.0f : xd(xa(-b, sq), a); }
+    else { inside = false; toi = t; }
+    return toi <= 3.402823466e+38f;
+}
+
+// local_ray_intersection_with_triangle (Ericson) — via TriMesh, reference call site src/shape/mesh.rs:67
+// `back`: bit0 = FeatureId::Face(1) (backface), bit2 (HF_NEGN) = normal is -normalize(n).
+__device__ __forceinline__ bool tri_cast(float3 a, float3 b, float3 c, float3 o, float3 d, float& toi, uint32_t& back) {
+    float3 ab = xsub(b, a), ac = xsub(c, a);
+    float3 n = xcross(ab, ac);
+    float dn = xdot(n, d);
+    if (dn == 0.0f) return false;
+    float3 ap = xsub(o, a);
+    float t = xdot(ap, n);
+    if ((t < 0.0f && dn < 0.0f) || (t > 0.0f && dn > 0.0f)) return false;
+    back = dn < 0.0f ? 0u : 1u;
+    dn = fabsf(dn);
+    float3 e = xcross(xneg(d), ap);
+    float v, w;
+    if (t < 0.0f) {
+        v = -xdot(ac, e); if (v < 0.0f || v > dn) return false;
+        w = xdot(ab, e);  if (w < 0.0f || xa(v, w) > dn) return false;
+        toi = xm(-t, xd(1.0f, dn));
+        back |= HF_NEGN;
+    } else {
+        v = xdot(ac, e);  if (v < 0.0f || v > dn) return false;
+        w = -xdot(ab, e); if (w < 0.0f || xa(v, w) > dn) return false;
+        toi = xm(t, xd(1.0f, dn));
+    }
+    return toi <= 3.402823466e+38f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// wide-BVH traversal (8-wide quantised nodes, octant-ordered, stack of (node group, hit mask))
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t sign_extend_s8x4(uint32_t x) { uint32_t r; asm("prmt.b32 %0, %1, 0x0, 0x0000BA98;" : "=r"(r) : "r"(x)); return r; }
+__device__ __forceinline__ uint32_t byte_of(uint32_t x, int j) { return (x >> (8 * j)) & 0xffu; }
+__device__ __forceinline__ uint32_t bfind(uint32_t x) { return 31u - __clz(x); }
+
+struct TravStats { uint32_t nodes, tris; };
+struct MeshHit { float t; uint32_t prim, face, back; };
+enum { TM_CLOSEST = 0, TM_ANY_LE = 1, TM_ANY_GT = 2 };
+constexpr int kStack = 28;
+
+struct WideRay {        // per-ray constants of the node test
+    float3 o, d, idir; uint32_t octinv4;
+};
+__device__ __forceinline__ WideRay make_wide_ray(float3 o, float3 d) {
+    WideRay r; r.o = o; r.d = d;
+    const float eps = 1e-20f;
+    r.idir.x = 1.0f / (fabsf(d.x) > eps ? d.x : copysignf(eps, d.x));
+    r.idir.y = 1.0f / (fabsf(d.y) > eps ? d.y : copysignf(eps, d.y));
+    r.idir.z = 1.0f / (fabsf(d.z) > eps ? d.z : copysignf(eps, d.z));
+    uint32_t oct = (d.x < 0.0f ? 4u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 1u : 0u);
+    r.octinv4 = (7u - oct) * 0x01010101u;
+    return r;
+}
+
+// Intersect the 8 children of one node; returns hit mask: bits 24..31 internal children in
+// traversal priority order, bits 0..23 leaf primitives.  [tmin, tmax] is the live ray interval.
+__device__ __forceinline__ uint32_t node_test(const float4* __restrict__ nodes, uint32_t node_index, const WideRay& r,
+                                              float tmin, float tmax, uint2& ngroup, uint2& tgroup) {
+    const float4* np = nodes + (size_t)node_index * 5;
+    const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+    const uint32_t ew = __float_as_uint(n0.w);
+    const float ax = __uint_as_float((ew & 0xffu) << 23) * r.idir.x;
+    const float ay = __uint_as_float(((ew >> 8) & 0xffu) << 23) * r.idir.y;
+    const float az = __uint_as_float(((ew >> 16) & 0xffu) << 23) * r.idir.z;
+    const float bx = (n0.x - r.o.x) * r.idir.x, by = (n0.y - r.o.y) * r.idir.y, bz = (n0.z - r.o.z) * r.idir.z;
+    // conservative padding: rounding of q*a + b is bounded by ~ulp(|b| + 255|a|)
+    const float px = fmaf(fabsf(ax), 255.0f, fabsf(bx)) * 2.4e-7f;
+    const float py = fmaf(fabsf(ay), 255.0f, fabsf(by)) * 2.4e-7f;
+    const float pz = fmaf(fabsf(az), 255.0f, fabsf(bz)) * 2.4e-7f;
+    const float blx = bx - px, bhx = bx + px, bly = by - py, bhy = by + py, blz = bz - pz, bhz = bz + pz;
+    uint32_t hitmask = 0;
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        const uint32_t meta4 = __float_as_uint(half == 0 ? n1.z : n1.w);
+        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+        const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
+        const uint32_t bit_index4 = (meta4 ^ (r.octinv4 & inner_mask4)) & 0x1F1F1F1Fu;
+        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+        const uint32_t qlox = __float_as_uint(half == 0 ? n2.x : n2.y), qloy = __float_as_uint(half == 0 ? n2.z : n2.w);
+        const uint32_t qloz = __float_as_uint(half == 0 ? n3.x : n3.y), qhix = __float_as_uint(half == 0 ? n3.z : n3.w);
+        const uint32_t qhiy = __float_as_uint(half == 0 ? n4.x : n4.y), qhiz = __float_as_uint(half == 0 ? n4.z : n4.w);
+        const uint32_t xn = r.d.x < 0.0f ? qhix : qlox, xf = r.d.x < 0.0f ? qlox : qhix;
+        const uint32_t yn = r.d.y < 0.0f ? qhiy : qloy, yf = r.d.y < 0.0f ? qloy : qhiy;
+        const uint32_t zn = r.d.z < 0.0f ? qhiz : qloz, zf = r.d.z < 0.0f ? qloz : qhiz;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float t0x = fmaf((float)byte_of(xn, j), ax, blx), t1x = fmaf((float)byte_of(xf, j), ax, bhx);
+            const float t0y = fmaf((float)byte_of(yn, j), ay, bly), t1y = fmaf((float)byte_of(yf, j), ay, bhy);
+            const float t0z = fmaf((float)byte_of(zn, j), az, blz), t1z = fmaf((float)byte_of(zf, j), az, bhz);
+            const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
+            const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
+            if (cmin <= cmax) hitmask |= byte_of(child_bits4, j) << byte_of(bit_index4, j);
+        }
+    }
+    ngroup.x = __float_as_uint(n1.x); tgroup.x = __float_as_uint(n1.y);
+    ngroup.y = (hitmask & 0xFF000000u) | (ew >> 24);
+    tgroup.y = hitmask & 0x00FFFFFFu;
+    return hitmask;
+}
+
+// Traverse one mesh BLAS in object space.
+//  TM_CLOSEST: mh = closest triangle with toi <= limit (ties: lowest face index); limit prunes.
+//  TM_ANY_LE : true as soon as a triangle with toi <= limit is found.
+//  TM_ANY_GT : true as soon as a triangle with toi >  limit is found.
+template <int MODE, bool STATS>
+__device__ __forceinline__ bool traverse_mesh(const float4* __restrict__ nodes, const float4* __restrict__ tris, uint32_t root,
+                                              float3 o, float3 d, float limit, MeshHit& mh, TravStats& st) {
+    const WideRay r = make_wide_ray(o, d);
+    uint2 stack[kStack]; int sp = 0;
+    uint2 ngroup = make_uint2(root, 0x80000000u), tgroup = make_uint2(0u, 0u);
+    float tmin = (MODE == TM_ANY_GT) ? limit : 0.0f;
+    float tmax = (MODE == TM_ANY_GT) ? 3.402823466e+38f : limit;
+    bool found = false;
+    if (MODE == TM_CLOSEST) { mh.t = 3.402823466e+38f; mh.face = 0xFFFFFFFFu; }
+    for (;;) {
+        if (ngroup.y > 0x00FFFFFFu) {
+            const uint32_t hits = ngroup.y, imask = ngroup.y;
+            const uint32_t cbit = bfind(hits);
+            const uint32_t base = ngroup.x;
+            ngroup.y &= ~(1u << cbit);
+            if (ngroup.y > 0x00FFFFFFu) { stack[sp++] = ngroup; }
+            const uint32_t slot = (cbit - 24u) ^ (r.octinv4 & 0xffu);
+            const uint32_t rel = __popc(imask & ~(0xFFFFFFFFu << slot));
+            if (STATS) st.nodes++;
+            node_test(nodes, base + rel, r, tmin, tmax, ngroup, tgroup);
+        } else {
+            tgroup = ngroup; ngroup = make_uint2(0u, 0u);
+        }
+        while (tgroup.y != 0u) {
+            const uint32_t ti = bfind(tgroup.y);
+            tgroup.y &= ~(1u << ti);
+            const uint32_t prim = tgroup.x + ti;
+            const float4* tp = tris + (size_t)prim * 3;
+            const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+            if (STATS) st.tris++;
+            float toi; uint32_t back;
+            if (tri_cast(f3(v0.x, v0.y, v0.z), f3(v1.x, v1.y, v1.z), f3(v2.x, v2.y, v2.z), o, d, toi, back)) {
+                if (MODE == TM_CLOSEST) {
+                    const uint32_t face = __float_as_uint(v0.w);
+                    if (toi < mh.t || (toi == mh.t && face < mh.face)) {
+                        if (toi <= limit) { mh.t = toi; mh.prim = prim; mh.face = face; mh.back = back; found = true; tmax = toi; }
+                    }
+                } else if (MODE == TM_ANY_LE) {
+                    if (toi <= limit) return true;
+                } else {
+                    if (toi > limit) return true;
+                }
+            }
+        }
+        if (ngroup.y <= 0x00FFFFFFu) {
+            if (sp == 0) break;
+            ngroup = stack[--sp];
+        }
+    }
+    return found;
+}
+
+// ------------------------------------------------------------------------------------------------
+// item level: Raytracing::trace (reference src/raytracing.rs:429-490)
+// ------------------------------------------------------------------------------------------------
+struct Best { float t; float key; uint32_t item, prim, flags; };
+
+__device__ __forceinline__ bool item_passes(uint32_t flags, bool for_shadow, uint32_t depth) {
+    // raytracing.rs:454: visible && cache.alpha > 0 && (!for_shadow || cast_shadow) && (!reflection_only || depth > 1)
+    if (!(flags & IF_VISIBLE) || !(flags & IF_ALPHA_POS)) return false;
+    if (for_shadow && !(flags & IF_CAST_SHADOW)) return false;
+    if ((flags & IF_REFL_ONLY) && depth <= 1) return false;
+    return true;
+}
+__device__ __forceinline__ bool item_solid(uint32_t flags, bool force_not_solid) {
+    // sphere.rs:49-50 / mesh.rs:55-56 (the cache never has an alpha texture)
+    return !(flags & IF_ALPHA_LT1) && (flags & IF_BACKFACE) && !force_not_solid;
+}
+
+// closest hit of one item, merged into `best` with the reference's order rule: strictly smaller t
+// wins; equal t -> smaller (bbox key, item index) = earlier in the stable sort of :466.
+template <bool STATS>
+__device__ __forceinline__ void visit_item_closest(const SceneDev& S, uint32_t ii, float3 o, float3 d, bool for_shadow, uint32_t depth,
+                                                   Best& best, TravStats& st, uint32_t& n_items, uint32_t& n_sph) {
+    const DItem* it = S.items + ii;
+    const uint32_t flags = it->flags;
+    if (!item_passes(flags, for_shadow, depth)) return;
+    float4 inv[3] = {__ldg(&it->inv[0]), __ldg(&it->inv[1]), __ldg(&it->inv[2])};
+    const float3 lo3 = xform_point(inv, o), ld3 = xform_vec(inv, d);
+    const float4 lo = __ldg(&it->lo), hi = __ldg(&it->hi);
+    const bool solid = item_solid(flags, for_shadow);
+    float key;
+    if (STATS) n_items++;
+    if (!aabb_cast(f3(lo.x, lo.y, lo.z), f3(hi.x, hi.y, hi.z), lo3, ld3, solid, key)) return;
+    float t; uint32_t prim = 0, hf = 0;
+    if (flags & IF_MESH) {
+        MeshHit mh;
+        if (!traverse_mesh<TM_CLOSEST, STATS>(S.nodes, S.tris, it->root, lo3, ld3, best.t, mh, st)) return;
+        t = mh.t; prim = mh.prim; hf = mh.back;
+    } else {
+        bool inside;
+        if (STATS) n_sph++;
+        if (!ball_cast(lo.w, lo3, ld3, solid, t, inside)) return;
+        hf = inside ? HF_INSIDE : 0u;
+    }
+    if (best.item == 0xFFFFFFFFu || t < best.t || (t == best.t && (key < best.key || (key == best.key && ii < best.item)))) {
+        best.t = t; best.key = key; best.item = ii; best.prim = prim; best.flags = hf;
+    }
+}
+
+// Closest hit over the whole scene (stop_on_first_hit = false).
+template <bool STATS>
+__device__ __forceinline__ void trace_closest(const SceneDev& S, float3 o, float3 d, bool for_shadow, uint32_t depth, Best& best,
+                                              TravStats& st, uint32_t& n_items, uint32_t& n_sph) {
+    best.t = 3.402823466e+38f; best.key = 0.0f; best.item = 0xFFFFFFFFu; best.prim = 0; best.flags = 0;
+    if (!S.use_tlas) {
+        for (uint32_t i = 0; i < S.n_items; i++) visit_item_closest<STATS>(S, i, o, d, for_shadow, depth, best, st, n_items, n_sph);
+        return;
+    }
+    const WideRay r = make_wide_ray(o, d);
+    uint2 stack[16]; int sp = 0;
+    uint2 ngroup = make_uint2(S.tlas_root, 0x80000000u), tgroup = make_uint2(0u, 0u);
+    for (;;) {
+        if (ngroup.y > 0x00FFFFFFu) {
+            const uint32_t hits = ngroup.y, imask = ngroup.y;
+            const uint32_t cbit = bfind(hits);
+            const uint32_t base = ngroup.x;
+            ngroup.y &= ~(1u << cbit);
+            if (ngroup.y > 0x00FFFFFFu) stack[sp++] = ngroup;
+            const uint32_t slot = (cbit - 24u) ^ (r.octinv4 & 0xffu);
+            const uint32_t rel = __popc(imask & ~(0xFFFFFFFFu << slot));
+            if (STATS) st.nodes++;
+            node_test(S.nodes, base + rel, r, 0.0f, best.t, ngroup, tgroup);
+        } else { tgroup = ngroup; ngroup = make_uint2(0u, 0u); }
+        while (tgroup.y != 0u) {
+            const uint32_t ti = bfind(tgroup.y);
+            tgroup.y &= ~(1u << ti);
+            visit_item_closest<STATS>(S, __ldg(S.tlas_prims + tgroup.x + ti), o, d, for_shadow, depth, best, st, n_items, n_sph);
+        }
+        if (ngroup.y <= 0x00FFFFFFu) { if (sp == 0) break; ngroup = stack[--sp]; }
+    }
+}
+
+// ---- shadow rays: trace(.., stop_on_first_hit = true, for_shadow = true) ---------------------------
+// The reference returns the CLOSEST hit of the FIRST item, in stable bbox-key order, that is hit at
+// all (raytracing.rs:466-487).  Candidates are produced kCand at a time in (key, index) order.
+constexpr int kCand = 8;
+struct CandList { float key[kCand]; uint32_t item[kCand]; int n; bool more; };
+
+__device__ __forceinline__ void cand_consider(const SceneDev& S, uint32_t ii, float3 o, float3 d, uint32_t depth, float ckey, uint32_t citem,
+                                              bool have_cursor, CandList& cl) {
+    const DItem* it = S.items + ii;
+    const uint32_t flags = it->flags;
+    if (!item_passes(flags, true, depth)) return;
+    float4 inv[3] = {__ldg(&it->inv[0]), __ldg(&it->inv[1]), __ldg(&it->inv[2])};
+    const float3 lo3 = xform_point(inv, o), ld3 = xform_vec(inv, d);
+    const float4 lo = __ldg(&it->lo), hi = __ldg(&it->hi);
+    float key;
+    if (!aabb_cast(f3(lo.x, lo.y, lo.z), f3(hi.x, hi.y, hi.z), lo3, ld3, false, key)) return;
+    if (have_cursor && (key < ckey || (key == ckey && ii <= citem))) return;     // already processed
+    // insert into the sorted bounded list
+    int pos = cl.n;
+    while (pos > 0 && (key < cl.key[pos - 1] || (key == cl.key[pos - 1] && ii < cl.item[pos - 1]))) pos--;
+    if (pos >= kCand) { cl.more = true; return; }
+    if (cl.n == kCand) cl.more = true;
+    int last = cl.n < kCand ? cl.n : kCand - 1;
+    for (int k = last; k > pos; k--) { cl.key[k] = cl.key[k - 1]; cl.item[k] = cl.item[k - 1]; }
+    cl.key[pos] = key; cl.item[pos] = ii;
+    if (cl.n < kCand) cl.n++;
+}
+
+__device__ __forceinline__ void collect_candidates(const SceneDev& S, float3 o, float3 d, uint32_t depth, float ckey, uint32_t citem,
+                                                   bool have_cursor, CandList& cl) {
+    cl.n = 0; cl.more = false;
+    if (!S.use_tlas) {
+        for (uint32_t i = 0; i < S.n_items; i++) cand_consider(S, i, o, d, depth, ckey, citem, have_cursor, cl);
+        return;
+    }
+    const WideRay r = make_wide_ray(o, d);
+    uint2 stack[16]; int sp = 0;
+    uint2 ngroup = make_uint2(S.tlas_root, 0x80000000u), tgroup = make_uint2(0u, 0u);
+    for (;;) {
+        if (ngroup.y > 0x00FFFFFFu) {
+            const uint32_t hits = ngroup.y, imask = ngroup.y;
+            const uint32_t cbit = bfind(hits);
+            const uint32_t base = ngroup.x;
+            ngroup.y &= ~(1u << cbit);
+            if (ngroup.y > 0x00FFFFFFu) stack[sp++] = ngroup;
+            const uint32_t slot = (cbit - 24u) ^ (r.octinv4 & 0xffu);
+            const uint32_t rel = __popc(imask & ~(0xFFFFFFFFu << slot));
+            node_test(S.nodes, base + rel, r, 0.0f, 3.402823466e+38f, ngroup, tgroup);
+        } else { tgroup = ngroup; ngroup = make_uint2(0u, 0u); }
+        while (tgroup.y != 0u) {
+            const uint32_t ti = bfind(tgroup.y);
+            tgroup.y &= ~(1u << ti);
+            cand_consider(S, __ldg(S.tlas_prims + tgroup.x + ti), o, d, depth, ckey, citem, have_cursor, cl);
+        }
+        if (ngroup.y <= 0x00FFFFFFu) { if (sp == 0) break; ngroup = stack[--sp]; }
+    }
+}
+
+// one item, shadow semantics (force_not_solid = true)
+template <int MODE, bool STATS>
+__device__ __forceinline__ bool item_shadow_test(const SceneDev& S, uint32_t ii, float3 o, float3 d, float limit, MeshHit& mh, uint32_t& hf,
+                                                 TravStats& st) {
+    const DItem* it = S.items + ii;
+    float4 inv[3] = {__ldg(&it->inv[0]), __ldg(&it->inv[1]), __ldg(&it->inv[2])};
+    const float3 lo3 = xform_point(inv, o), ld3 = xform_vec(inv, d);
+    if (it->flags & IF_MESH) {
+        bool h = traverse_mesh<MODE, STATS>(S.nodes, S.tris, it->root, lo3, ld3, limit, mh, st);
+        if (MODE == TM_CLOSEST && h) hf = mh.back;
+        return h;
+    }
+    float t; bool inside;
+    if (!ball_cast(__ldg(&it->lo).w, lo3, ld3, false, t, inside)) return false;
+    if (MODE == TM_CLOSEST) { mh.t = t; mh.prim = 0; mh.face = 0; mh.back = 0; hf = inside ? HF_INSIDE : 0u; return true; }
+    if (MODE == TM_ANY_LE) return t <= limit;
+    return t > limit;
+}
+
+// Literal restatement: per item in order, full closest hit; return the first item hit.
+template <bool STATS>
+__device__ __forceinline__ void trace_shadow_ordered(const SceneDev& S, float3 o, float3 d, uint32_t depth, Best& best, TravStats& st) {
+    best.item = 0xFFFFFFFFu; best.t = 3.402823466e+38f; best.prim = 0; best.flags = 0; best.key = 0.0f;
+    float ckey = 0.0f; uint32_t citem = 0; bool have = false;
+    CandList cl;
+    for (;;) {
+        collect_candidates(S, o, d, depth, ckey, citem, have, cl);
+        for (int k = 0; k < cl.n; k++) {
+            MeshHit mh; uint32_t hf = 0;
+            if (item_shadow_test<TM_CLOSEST, STATS>(S, cl.item[k], o, d, 3.402823466e+38f, mh, hf, st)) {
+                best.item = cl.item[k]; best.t = mh.t; best.prim = mh.prim; best.flags = hf; best.key = cl.key[k];
+                return;
+            }
+        }
+        if (!cl.more || cl.n == 0) return;
+        ckey = cl.key[cl.n - 1]; citem = cl.item[cl.n - 1]; have = true;
+    }
+}
+
+// Equivalent two-phase any-hit walk used by the shadow kernel.  `len` = light distance (+inf for
+// directional).  Result: occluder item (or ~0u when lit).  When the occluder's material has an
+// alpha texture the closest hit on it is also returned (needed for the attenuation lookup).
+//   phase 1: first item k in order with a hit at toi <= len          -> candidate occluder
+//   phase 2: an earlier item j < k with a hit at all (so toi > len)   -> the reference stops at j: lit
+template <bool STATS>
+__device__ __forceinline__ void trace_shadow_fast(const SceneDev& S, float3 o, float3 d, uint32_t depth, float len, Best& best, TravStats& st) {
+    best.item = 0xFFFFFFFFu; best.t = 3.402823466e+38f; best.prim = 0; best.flags = 0; best.key = 0.0f;
+    float ckey = 0.0f; uint32_t citem = 0; bool have = false;
+    CandList cl;
+    for (;;) {
+        collect_candidates(S, o, d, depth, ckey, citem, have, cl);
+        for (int k = 0; k < cl.n; k++) {
+            MeshHit mh; uint32_t hf = 0;
+            if (item_shadow_test<TM_ANY_LE, STATS>(S, cl.item[k], o, d, len, mh, hf, st)) {
+                // phase 2 over everything before (key, item) in order — only needed for finite len
+                if (len < 3.402823466e+38f) {
+                    const float kkey = cl.key[k]; const uint32_t kitem = cl.item[k];
+                    float c2 = 0.0f; uint32_t i2 = 0; bool h2 = false;
+                    CandList c;
+                    for (;;) {
+                        collect_candidates(S, o, d, depth, c2, i2, h2, c);
+                        bool done = false;
+                        for (int q = 0; q < c.n; q++) {
+                            if (!(c.key[q] < kkey || (c.key[q] == kkey && c.item[q] < kitem))) { done = true; break; }
+                            MeshHit m2; uint32_t f2;
+                            if (item_shadow_test<TM_ANY_GT, STATS>(S, c.item[q], o, d, len, m2, f2, st)) return;   // lit
+                        }
+                        if (done || !c.more || c.n == 0) break;
+                        c2 = c.key[c.n - 1]; i2 = c.item[c.n - 1]; h2 = true;
+                    }
+                }
+                best.item = cl.item[k]; best.key = cl.key[k]; best.t = 0.0f;
+                if (S.items[cl.item[k]].flags & IF_ALPHA_TEX) {
+                    item_shadow_test<TM_CLOSEST, STATS>(S, cl.item[k], o, d, 3.402823466e+38f, mh, hf, st);
+                    best.t = mh.t; best.prim = mh.prim; best.flags = hf;
+                }
+                return;
+            }
+        }
+        if (!cl.more || cl.n == 0) return;
+        ckey = cl.key[cl.n - 1]; citem = cl.item[cl.n - 1]; have = true;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// hit attributes: Sphere::intersect / Mesh::intersect normal, get_uv, get_normal
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float3 ld3(const float* p, uint32_t i) { return f3(__ldg(p + 3 * (size_t)i), __ldg(p + 3 * (size_t)i + 1), __ldg(p + 3 * (size_t)i + 2)); }
+
+// area-ratio weights of Mesh::get_uv / get_normal (reference src/shape/mesh.rs:105-161, 204-259)
+__device__ __forceinline__ void area_weights(const SceneDev& S, const DItem& it, float3 hit, uint32_t f_id, float w[3]) {
+    const float3 hl = xform_point(it.inv, hit);
+    const uint32_t* fi = S.idx + it.idx_off + 3 * (size_t)f_id;
+    const float3 a = ld3(S.verts + it.vert_off, __ldg(fi)), b = ld3(S.verts + it.vert_off, __ldg(fi + 1)), c = ld3(S.verts + it.vert_off, __ldg(fi + 2));
+    const float3 f1 = xsub(a, hl), f2 = xsub(b, hl), f3_ = xsub(c, hl);
+    const float area = xnorm(xcross(xsub(a, b), xsub(a, c)));
+    w[0] = xd(xnorm(xcross(f2, f3_)), area); w[1] = xd(xnorm(xcross(f3_, f1)), area); w[2] = xd(xnorm(xcross(f1, f2)), area);
+}
+
+__device__ __forceinline__ void item_get_uv(const SceneDev& S, const DItem& it, float3 hit, uint32_t face_id, float& u, float& v) {
+    const float PI = 3.14159265358979323846f;
+    if (!(it.flags & IF_MESH)) {                                  // sphere.rs:69-99
+        const float3 hl = xform_point(it.inv, hit);
+        const float theta = atan2f(-hl.z, hl.x);
+        u = (theta + PI) / (2.0f * PI);
+        const float phi = acosf((-hl.y) / it.lo.w);
+        v = -(phi / PI);
+        return;
+    }
+    const uint32_t f_id = face_id % it.n_faces;
+    if ((int32_t)it.n_uv_faces - 1 < (int32_t)f_id || (int32_t)it.n_faces - 1 < (int32_t)f_id) { u = 0.0f; v = 0.0f; return; }
+    float w[3]; area_weights(S, it, hit, f_id, w);
+    const uint32_t* ui = S.uv_idx + it.uvidx_off + 3 * (size_t)f_id;
+    const float* ua = S.uvs + it.uv_off + 2 * (size_t)__ldg(ui); const float* ub = S.uvs + it.uv_off + 2 * (size_t)__ldg(ui + 1);
+    const float* uc = S.uvs + it.uv_off + 2 * (size_t)__ldg(ui + 2);
+    u = xa(xa(xm(__ldg(ua), w[0]), xm(__ldg(ub), w[1])), xm(__ldg(uc), w[2]));
+    v = -xa(xa(xm(__ldg(ua + 1), w[0]), xm(__ldg(ub + 1), w[1])), xm(__ldg(uc + 1), w[2]));
+}
+
+// World-space shading normal returned by Shape::intersect (sphere.rs:54-67, mesh.rs:61-103) and the
+// reference face id (parry FeatureId: face, +n_faces on a backface).
+__device__ __forceinline__ float3 hit_normal(const SceneDev& S, const DItem& it, float3 o, float3 d, float t, uint32_t prim, uint32_t hflags,
+                                             uint32_t& face_id) {
+    if (!(it.flags & IF_MESH)) {
+        const float3 lo3 = xform_point(it.inv, o), ld = xform_vec(it.inv, d);
+        float3 n = xnormalize(xadd(lo3, xscale(ld, t)));
+        if ((hflags & HF_INSIDE) && S.ball_flip_inside) n = xneg(n);
+        face_id = 0;
+        return xnormalize(xform_vec(it.mat, n));
+    }
+    const float4* tp = S.tris + (size_t)prim * 3;
+    const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+    const uint32_t face = __float_as_uint(v0.w);
+    const bool back = hflags & HF_BACK;
+    face_id = back ? face + it.n_faces : face;
+    float3 n;
+    if ((it.flags & IF_SMOOTH) && (it.flags & IF_HAS_NORMALS)) {
+        const float3 hit = xadd(o, xscale(d, t));
+        float w[3]; area_weights(S, it, hit, face, w);
+        const uint32_t* ni = S.n_idx + it.nidx_off + 3 * (size_t)face;
+        const float3 a = ld3(S.nrms + it.nrm_off, __ldg(ni)), b = ld3(S.nrms + it.nrm_off, __ldg(ni + 1)), c = ld3(S.nrms + it.nrm_off, __ldg(ni + 2));
+        const float3 p1 = xscale(a, w[0]), p2 = xscale(b, w[1]), p3 = xscale(c, w[2]);
+        n = f3(xa(xa(p1.x, p2.x), p3.x), xa(xa(p1.y, p2.y), p3.y), xa(xa(p1.z, p2.z), p3.z));
+        n = xnormalize(xform_vec(it.mat, n));
+        if (back) n = xneg(n);
+    } else {
+        const float3 a = f3(v0.x, v0.y, v0.z), b = f3(v1.x, v1.y, v1.z), c = f3(v2.x, v2.y, v2.z);
+        float3 g = xnormalize(xcross(xsub(b, a), xsub(c, a)));
+        if (hflags & HF_NEGN) g = xneg(g);      // parry: normal faces the ray origin
+        n = xnormalize(xform_vec(it.mat, g));
+    }
+    if (it.flags & IF_FLIP) n = xneg(n);
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// textures (reference src/raytracing.rs:629-675, src/shape/mod.rs:510-629)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 texel_at(const SceneDev& S, const DTex& t, uint32_t x, uint32_t y) {
+    const size_t off = ((size_t)t.offset_hi << 32 | t.offset_lo) + (size_t)y * t.w + x;
+    const uchar4 p = __ldg(S.texels + off);
+    return make_float4((float)p.x / 255.0f, (float)p.y / 255.0f, (float)p.z / 255.0f, (float)p.w / 255.0f);
+}
+__device__ __forceinline__ uint32_t tex_wrap(float val, uint32_t bound) {
+    const int32_t sb = (int32_t)bound;
+    const int32_t w = as_i32(xm(val, (float)bound)) % sb;
+    return w < 0 ? (uint32_t)(w + sb) : (uint32_t)w;
+}
+__device__ __forceinline__ float lerp1(float a, float b, float f) { return xa(a, xm(f, xs(b, a))); }
+__device__ __forceinline__ float4 lerp4(float4 a, float4 b, float f) { return make_float4(lerp1(a.x, b.x, f), lerp1(a.y, b.y, f), lerp1(a.z, b.z, f), lerp1(a.w, b.w, f)); }
+__device__ __forceinline__ float4 tex_interpolate(const SceneDev& S, const DTex& t, float xf, float yf) {
+    float x = xm(xf, (float)t.w), y = xm(yf, (float)t.h);
+    if (x < 0.0f) x = xa(x, (float)t.w);
+    if (y < 0.0f) y = xa(y, (float)t.h);
+    uint32_t x0 = as_u32(floorf(x)), x1 = as_u32(ceilf(x)), y0 = as_u32(floorf(y)), y1 = as_u32(ceilf(y));
+    if (x0 >= t.w) x0 = t.w - 1; if (y0 >= t.h) y0 = t.h - 1;
+    if (x1 >= t.w) x1 = t.w - 1; if (y1 >= t.h) y1 = t.h - 1;
+    const float fx = xs(x, (float)x0), fy = xs(y, (float)y0);
+    const float4 a = lerp4(texel_at(S, t, x0, y0), texel_at(S, t, x1, y0), fx);
+    const float4 b = lerp4(texel_at(S, t, x0, y1), texel_at(S, t, x1, y1), fx);
+    return lerp4(a, b, fy);
+}
+// Raytracing::get_tex_color: false when the material has no such texture (or no uv)
+__device__ __forceinline__ bool get_tex_color(const SceneDev& S, const DMaterial& m, bool has_uv, float u, float v, int type, float4& out) {
+    const int ti = m.tex[type];
+    if (ti < 0 || !has_uv) return false;
+    const DTex t = S.texs[ti];
+    if (t.w == 0) return false;
+    out = m.nearest ? texel_at(S, t, tex_wrap(u, t.w), tex_wrap(v, t.h)) : tex_interpolate(S, t, u, v);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// shading helpers (reference src/raytracing.rs:492-626)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool create_transmission(float3 normal, float3 incident, float3 p, float index, float3& o, float3& d) {
+    float3 ref_n = normal; float eta_t = index, eta_i = 1.0f; float i_dot_n = dot3(incident, normal);
+    if (i_dot_n < 0.0f) i_dot_n = -i_dot_n; else { ref_n = -normal; eta_t = 1.0f; eta_i = index; }
+    const float eta = eta_i / eta_t;
+    const float k = 1.0f - (eta * eta) * (1.0f - i_dot_n * i_dot_n);
+    if (k < 0.0f) return false;
+    o = p + ref_n * (-0.001f);
+    d = (incident + i_dot_n * ref_n) * eta - ref_n * sqrtf(k);
+    return true;
+}
+__device__ __forceinline__ float fresnel(float3 incident, float3 normal, float index) {
+    const float i_dot_n = dot3(incident, normal);
+    float eta_i = 1.0f, eta_t = index;
+    if (i_dot_n > 0.0f) { eta_i = eta_t; eta_t = 1.0f; }
+    const float sin_t = eta_i / eta_t * sqrtf(fmaxf(1.0f - i_dot_n * i_dot_n, 0.0f));
+    if (sin_t > 1.0f) return 1.0f;
+    const float cos_t = sqrtf(fmaxf(1.0f - sin_t * sin_t, 0.0f));
+    const float cos_i = fabsf(cos_t);
+    const float r_s = ((eta_t * cos_i) - (eta_i * cos_t)) / ((eta_t * cos_i) + (eta_i * cos_t));
+    const float r_p = ((eta_i * cos_i) - (eta_t * cos_t)) / ((eta_i * cos_i) + (eta_t * cos_t));
+    return (r_s * r_s + r_p * r_p) / 2.0f;
+}
+__device__ __forceinline__ float3 jitter(float3 dir, float spread, uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t path, uint32_t slot) {
+    const float PI = 3.14159265358979323846f;
+    if (spread <= 0.0f) return dir;
+    const float3 b3 = norm3(dir);
+    const float3 diff = fabsf(b3.x) < 0.5f ? f3(1, 0, 0) : f3(0, 1, 0);
+    const float3 b1 = norm3(cross3(b3, diff));
+    const float3 b2 = cross3(b1, b3);
+    const float z_lo = cosf(spread * PI);
+    if (!(z_lo < 1.0f)) return dir;
+    const float z = z_lo + mc_uniform(seed, pixel, sample, path, slot) * (1.0f - z_lo);
+    const float r = sqrtf(1.0f - z * z);
+    const float theta = -PI + mc_uniform(seed, pixel, sample, path, slot + 1) * (PI - (-PI));
+    float sn, cs; sincosf(theta, &sn, &cs);
+    return norm3((r * cs) * b1 + (r * sn) * b2 + z * b3);
+}
+
+// warp-aggregated queue append: returns the slot of this lane (valid only where `emit`)
+__device__ __forceinline__ uint32_t queue_append(uint32_t* counter, bool emit) {
+    const uint32_t mask = __ballot_sync(__activemask(), emit);
+    if (!emit) return 0;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t leader = __ffs(mask) - 1u;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    return base + __popc(mask & ((1u << lane) - 1u));
+}
+
+}  // namespace rtx

@@ -1,0 +1,422 @@
+// rtx_kernels.cuh — the wavefront kernels of the ray-casting hot path (sm_100a).
+//
+//   K1 raygen_kernel        Raytracing::render ray generation        (reference src/raytracing.rs:319-396)
+//   K2 closest_kernel       Raytracing::trace, closest hit            (:429-490, called at :726)
+//   K4 shade_kernel         get_color_depth_normal_id body            (:720-998), emits shadow + child rays
+//   K3 shadow_kernel        Raytracing::trace, stop_on_first_hit      (:883-913) + light accumulation (:917-919)
+//   K6 resolve_kernel       mean / clamp / u8 / gamma / normalize     (:406-426) -> the four frame buffers
+//   probe_kernel            Raytracing::trace as a test hook (rtx_trace_probe)
+//
+// The recursion of get_color_depth_normal_id is linear in the two child radiances with scalar
+// coefficients, so each queued ray carries one float of throughput:
+//   local = (1-f)·ao·a·(1-ρ)·D + ao·f·fog + E ;  w_R = w·(1-f)·ao·a·ρ ;  w_T = w·(1-f)·ao·kt
+#pragma once
+#include "rtx_device.cuh"
+
+namespace rtx {
+
+constexpr int kTraceBlock = 128;
+constexpr int kShadeBlock = 128;
+
+struct WorkCtr { uint32_t* next; };    // one zeroed counter per launch (dynamic warp-granular fetch)
+
+// ---- K1 ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mul4(const float* m, float x, float y, float z, float w, float out[4]) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) out[r] = xa(xa(xa(xm(m[r], x), xm(m[4 + r], y)), xm(m[8 + r], z)), xm(m[12 + r], w));
+}
+
+__device__ __forceinline__ void gen_ray(const FrameDev& F, uint32_t px, uint32_t py, uint32_t x_i, uint32_t y_i, float3& o, float3& d) {
+    const float x_f = (float)px, y_f = (float)py, w = (float)F.width, h = (float)F.height;
+    const float x_step = xd(2.0f, w), y_step = xd(2.0f, h);
+    const float inv_cell = xd(1.0f, (float)F.cell_size);
+    float x_trans = xm(xm(x_step, (float)x_i), inv_cell);
+    float y_trans = xm(xm(y_step, (float)y_i), inv_cell);
+    const bool dof = F.aperture_size > 1.0f && F.focal_length > 1.0f;
+    if (dof && F.n_samples > 1) { x_trans = xs(x_trans, xd(x_step, 2.0f)); y_trans = xs(y_trans, xd(y_step, 2.0f)); }
+    const float cx = xs(xm(xd(xa(x_f, 0.5f), w), 2.0f), 1.0f), cy = xs(1.0f, xm(xd(xa(y_f, 0.5f), h), 2.0f));
+    float pp[4], o4[4], d4[4];
+    if (dof) {                                                                   // :338-377
+        const float aperture_scale = xd((float)F.width, 800.0f);
+        x_trans = xm(x_trans, xm(F.aperture_size, aperture_scale));
+        y_trans = xm(y_trans, xm(F.aperture_size, aperture_scale));
+        mul4(F.pinv, cx, cy, -1.0f, 1.0f, pp); pp[3] = 1.0f;
+        const float rd[3] = {xs(pp[0], 0.0f), xs(pp[1], 0.0f), xs(pp[2], 0.0f)};
+        float origin[4], dir[4];
+        mul4(F.vinv, 0.0f, 0.0f, 0.0f, 1.0f, origin);
+        mul4(F.vinv, rd[0], rd[1], rd[2], 0.0f, dir);
+        const float n4 = xsqrt(xa(xa(xm(dir[0], dir[0]), xm(dir[2], dir[2])), xa(xm(dir[1], dir[1]), xm(dir[3], dir[3]))));
+        for (int i = 0; i < 4; i++) dir[i] = xd(dir[i], n4);
+        const float dist = xnorm(f3(rd[0], rd[1], rd[2]));
+        const float f = xd(1.0f, xd(dist, xa(dist, F.focal_length)));
+        float p[3]; for (int i = 0; i < 3; i++) p[i] = xa(origin[i], xm(f, dir[i]));
+        mul4(F.pinv, xa(cx, x_trans), xa(cy, y_trans), -1.0f, 1.0f, pp); pp[3] = 1.0f;
+        mul4(F.vinv, pp[0], pp[1], pp[2], pp[3], o4);
+        o = f3(o4[0], o4[1], o4[2]);
+        d = f3(xs(p[0], o4[0]), xs(p[1], o4[1]), xs(p[2], o4[2]));
+        return;
+    }
+    mul4(F.pinv, xa(cx, x_trans), xa(cy, y_trans), -1.0f, 1.0f, pp); pp[3] = 1.0f;   // :381-395
+    mul4(F.vinv, pp[0], pp[1], pp[2], pp[3], o4);
+    mul4(F.vinv, xs(pp[0], 0.0f), xs(pp[1], 0.0f), xs(pp[2], 0.0f), 0.0f, d4);
+    o = f3(o4[0], o4[1], o4[2]); d = f3(d4[0], d4[1], d4[2]);
+}
+
+// batch = pixels [p0, p0+np) of the owned pixel list x samples [s0, s0+ns); ray i -> (s0 + i/np, p0 + i%np)
+__global__ void __launch_bounds__(256) raygen_kernel(FrameDev F, const uint32_t* __restrict__ pixel_list, uint32_t p0, uint32_t np, uint32_t s0,
+                                                     uint32_t ns, RayQ q, uint32_t q_base) {
+    const uint32_t n = np * ns;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t s = s0 + i / np, pi = p0 + i % np;
+        const uint32_t pixel = __ldg(pixel_list + pi);
+        const ushort2 xy = F.sample_table[s];
+        float3 o, d;
+        gen_ray(F, pixel % F.width, pixel / F.width, xy.x, xy.y, o, d);
+        d = xnormalize(d);                                                       // :722-723
+        const uint32_t flags = (s == F.n_samples - 1) ? RF_ID_OWNER : 0u;
+        q.o[q_base + i] = make_float4(o.x, o.y, o.z, 1.0f);
+        q.d[q_base + i] = make_float4(d.x, d.y, d.z, __uint_as_float(pixel));
+        q.m[q_base + i] = make_uint2((s & 0xffffu) | (1u << 16) | (flags << 24), 1u);
+    }
+}
+
+// ---- K2 ------------------------------------------------------------------------------------------
+template <bool STATS>
+__global__ void __launch_bounds__(kTraceBlock) closest_kernel(SceneDev S, RayQ q, uint32_t q_base, uint32_t n, HitRec* __restrict__ hits,
+                                                              uint32_t* work, Counters* ctr) {
+    TravStats st{0, 0}; uint32_t n_items = 0, n_sph = 0;
+    const uint32_t lane = threadIdx.x & 31u;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(work, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t i = base + lane;
+        if (i < n) {
+            const float4 ro = q.o[q_base + i], rd = q.d[q_base + i];
+            const uint32_t depth = (q.m[q_base + i].x >> 16) & 0xffu;
+            Best best;
+            trace_closest<STATS>(S, f3(ro.x, ro.y, ro.z), f3(rd.x, rd.y, rd.z), false, depth, best, st, n_items, n_sph);
+            HitRec h; h.t = best.t; h.item = best.item; h.prim = best.prim; h.flags = best.flags;
+            hits[i] = h;
+        }
+    }
+    if (STATS) {
+        atomicAdd(&ctr->node_visits, (unsigned long long)st.nodes); atomicAdd(&ctr->tri_tests, (unsigned long long)st.tris);
+        atomicAdd(&ctr->item_tests, (unsigned long long)n_items); atomicAdd(&ctr->sphere_tests, (unsigned long long)n_sph);
+    }
+}
+
+// ---- K3 ------------------------------------------------------------------------------------------
+template <bool STATS, bool ORDERED>
+__global__ void __launch_bounds__(kTraceBlock) shadow_kernel(SceneDev S, FrameDev F, ShadowQ q, const uint32_t* __restrict__ n_ptr, uint32_t depth,
+                                                             uint32_t* work, Counters* ctr) {
+    TravStats st{0, 0};
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n = *n_ptr;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(work, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t i = base + lane;
+        if (i < n) {
+            const float4 ro = q.o[i], rd = q.d[i], rc = q.c[i];
+            const float3 o = f3(ro.x, ro.y, ro.z), d = f3(rd.x, rd.y, rd.z);
+            const float len = ro.w;
+            const uint32_t pixel = __float_as_uint(rd.w);
+            Best b;
+            bool in_light;
+            if (ORDERED) {
+                trace_shadow_ordered<STATS>(S, o, d, depth, b, st);
+                in_light = b.item == 0xFFFFFFFFu || b.t > len;                  // :885-892 (len = +inf for directional)
+            } else {
+                trace_shadow_fast<STATS>(S, o, d, depth, len, b, st);
+                in_light = b.item == 0xFFFFFFFFu;
+            }
+            float k = 1.0f;
+            if (!in_light) {                                                    // :895-913
+                float ssa = rc.w;
+                const DItem& occ = S.items[b.item];
+                if (occ.flags & IF_ALPHA_TEX) {
+                    const DItem& recv = S.items[q.r[i]];
+                    uint32_t face_id = 0;
+                    if (occ.flags & IF_MESH) {
+                        const uint32_t face = __float_as_uint(__ldg(S.tris + (size_t)b.prim * 3).w);
+                        face_id = (b.flags & HF_BACK) ? face + occ.n_faces : face;
+                    }
+                    const float3 shp = o + d * b.t;
+                    float u, v; item_get_uv(S, recv, shp, face_id, u, v);        // receiver's get_uv (sic, :905)
+                    float4 tc;
+                    if (get_tex_color(S, S.mats[occ.material], true, u, v, 4 /*Alpha*/, tc)) ssa *= tc.x;
+                }
+                k = 1.0f - ssa;
+            }
+            atomicAdd(&F.accum_c[pixel], make_float4(rc.x * k, rc.y * k, rc.z * k, 0.0f));
+        }
+    }
+    if (STATS) { atomicAdd(&ctr->node_visits, (unsigned long long)st.nodes); atomicAdd(&ctr->tri_tests, (unsigned long long)st.tris); }
+}
+
+// ---- K4 ------------------------------------------------------------------------------------------
+struct ShadeOut {
+    RayQ child; uint32_t child_cap; uint32_t* child_count;      // level d+1 queue
+    ShadowQ shadow; uint32_t shadow_cap; uint32_t* shadow_count;
+    uint32_t* overflow;                                         // set to 1 if a queue would overflow (never, by construction)
+};
+
+__global__ void __launch_bounds__(kShadeBlock) shade_kernel(SceneDev S, FrameDev F, RayQ q, uint32_t q_base, uint32_t n, const HitRec* __restrict__ hits,
+                                                            ShadeOut out) {
+    const float PI = 3.14159265358979323846f;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const bool active = i < n;
+        // --- load ---
+        float3 o = f3(0, 0, 0), d = f3(0, 0, 1); float wgt = 0.0f; uint32_t pixel = 0, sample = 0, depth = 1, rflags = 0, path = 1;
+        HitRec h; h.item = 0xFFFFFFFFu; h.t = 0; h.prim = 0; h.flags = 0;
+        if (active) {
+            const float4 ro = q.o[q_base + i], rd = q.d[q_base + i]; const uint2 m = q.m[q_base + i];
+            o = f3(ro.x, ro.y, ro.z); d = f3(rd.x, rd.y, rd.z); wgt = ro.w; pixel = __float_as_uint(rd.w);
+            sample = m.x & 0xffffu; depth = (m.x >> 16) & 0xffu; rflags = m.x >> 24; path = m.y;
+            h = hits[i];
+        }
+        const bool hit = active && h.item != 0xFFFFFFFFu;
+        if (active && !hit && (rflags & RF_ID_OWNER)) F.ids[pixel] = 0u;
+
+        bool emit_refl = false, emit_trans = false;
+        float3 refl_o, refl_d, trans_o, trans_d; float w_refl = 0.0f, w_trans = 0.0f; uint32_t trans_flags = 0;
+        // per-light shadow payloads are produced inside the light loop (warp-aggregated per light)
+        float3 hit_point = f3(0, 0, 0), surface_normal = f3(0, 0, 1); float coef_d = 0.0f;
+        float4 base_color = make_float4(0, 0, 0, 0), specular_color = make_float4(0, 0, 0, 0);
+        float shininess = 0.0f, mat_alpha = 1.0f, shadow_softness = 0.0f; bool recv_shadow = false, mat_mc = false;
+        float3 direct = f3(0, 0, 0), constant = f3(0, 0, 0);
+
+        if (hit) {
+            const DItem& item = S.items[h.item];
+            const DMaterial& mat = S.mats[item.material];
+            uint32_t face_id;
+            const float3 normal = hit_normal(S, item, o, d, h.t, h.prim, h.flags, face_id);
+            const float hit_dist = h.t;
+            if (depth == 1) {                                                    // :400-403 depth / normal sums
+                atomicAdd(&F.accum_c[pixel], make_float4(0.0f, 0.0f, 0.0f, hit_dist));
+                atomicAdd(&F.accum_n[pixel], make_float4(normal.x, normal.y, normal.z, 0.0f));
+            }
+            if (rflags & RF_ID_OWNER) F.ids[pixel] = item.id;
+            surface_normal = normal;
+            hit_point = o + (d * hit_dist);
+            const bool has_uv = mat.any_texture != 0;
+            float u = 0.0f, v = 0.0f;
+            if (has_uv) item_get_uv(S, item, hit_point, face_id, u, v);
+            float4 tc;
+            if (get_tex_color(S, mat, has_uv, u, v, 3 /*Normal*/, tc)) {          // :757-784
+                float3 tangent = cross3(normal, f3(0, 1, 0));
+                if (len3(tangent) <= 0.0001f) tangent = cross3(normal, f3(0, 0, 1));
+                tangent = norm3(tangent);
+                const float3 bitangent = norm3(cross3(normal, tangent));
+                float3 nm = f3(tc.x * 2.0f - 1.0f, tc.y * 2.0f - 1.0f, tc.z * 2.0f - 1.0f);
+                nm.x *= mat.normal_map_strength; nm.y *= mat.normal_map_strength;
+                nm = norm3(nm);
+                surface_normal = norm3(f3((tangent.x * nm.x + bitangent.x * nm.y) + normal.x * nm.z,
+                                          (tangent.y * nm.x + bitangent.y * nm.y) + normal.y * nm.z,
+                                          (tangent.z * nm.x + bitangent.z * nm.y) + normal.z * nm.z));
+            }
+            const bool has_rough = get_tex_color(S, mat, has_uv, u, v, 5 /*Roughness*/, tc);   // :787-798
+            if (F.monte_carlo && mat.monte_carlo && (mat.roughness > 0.0f || has_rough)) {
+                float roughness = mat.roughness;
+                if (has_rough) roughness = (1.0f / PI / 2.0f) * tc.x;
+                surface_normal = jitter(surface_normal, roughness, F.mc_seed, pixel, sample, path, 0);
+            }
+            float4 ambient_color = make_float4(mat.ambient[0], mat.ambient[1], mat.ambient[2], 1.0f);   // :801-803
+            if (get_tex_color(S, mat, has_uv, u, v, 1 /*AmbientEmissive*/, tc)) { ambient_color.x *= tc.x; ambient_color.y *= tc.y; ambient_color.z *= tc.z; }
+            base_color = make_float4(mat.base[0], mat.base[1], mat.base[2], 1.0f);
+            if (get_tex_color(S, mat, has_uv, u, v, 0 /*Base*/, tc)) { base_color.x *= tc.x; base_color.y *= tc.y; base_color.z *= tc.z; base_color.w *= tc.w; }
+            specular_color = make_float4(mat.specular[0], mat.specular[1], mat.specular[2], 1.0f);
+            if (get_tex_color(S, mat, has_uv, u, v, 2 /*Specular*/, tc)) { specular_color.x *= tc.x; specular_color.y *= tc.y; specular_color.z *= tc.z; }
+            float alpha = mat.alpha * base_color.w;                                // :806-811
+            if (get_tex_color(S, mat, has_uv, u, v, 4 /*Alpha*/, tc)) alpha *= tc.x;
+
+            const float kr = fresnel(d, surface_normal, mat.refraction_index);   // :925
+            float reflectivity = mat.reflectivity;                                // :928-933
+            if (get_tex_color(S, mat, has_uv, u, v, 7 /*Reflectivity*/, tc)) reflectivity = tc.x;
+            const bool can_recurse = depth <= F.max_recursion;
+            const bool reflect_on = reflectivity > 0.0f && can_recurse;           // :938
+            bool trans_exists = false;
+            if (alpha < 1.0f && can_recurse)                                      // :948-952
+                trans_exists = create_transmission(surface_normal, d, hit_point, mat.refraction_index, trans_o, trans_d);
+            const float a = trans_exists ? alpha : ((alpha < 1.0f && !can_recurse) ? alpha : 1.0f);   // :959-975 (TIR keeps 1)
+            const float kt = trans_exists ? ((kr < 1.0f ? (1.0f - kr) : 1.0f) * (1.0f - alpha)) : 0.0f;
+            const float fog = fminf(F.fog_density * hit_dist, 1.0f);              // :978-982
+            float ao = 1.0f;
+            if (get_tex_color(S, mat, has_uv, u, v, 6 /*AmbientOcclusion*/, tc)) ao = tc.x;   // :985-991
+            const float thru = wgt * ao * (1.0f - fog);
+            coef_d = thru * a * (1.0f - reflectivity);
+            constant = f3(wgt * (ao * fog * F.fog_color[0] + ambient_color.x), wgt * (ao * fog * F.fog_color[1] + ambient_color.y),
+                          wgt * (ao * fog * F.fog_color[2] + ambient_color.z));
+            if (reflect_on) {                                                     // :492-498
+                emit_refl = true; w_refl = thru * a * reflectivity;
+                refl_o = hit_point + surface_normal * 0.001f;
+                refl_d = d - (2.0f * dot3(d, surface_normal)) * surface_normal;
+            }
+            if (trans_exists) {
+                emit_trans = true; w_trans = thru * kt;
+                if ((rflags & RF_ID_OWNER) && approx_equal(alpha, 0.0f)) trans_flags = RF_ID_OWNER;   // :966-969
+            }
+            shininess = mat.shininess; mat_alpha = mat.alpha; shadow_softness = mat.shadow_softness;
+            recv_shadow = mat.receive_shadow != 0; mat_mc = mat.monte_carlo != 0;
+        }
+
+        // --- lights (:814-920): one warp-aggregated shadow-queue append per light ---
+        for (uint32_t li = 0; li < S.n_lights; li++) {
+            const DLight& L = S.lights[li];
+            if (!L.enabled) continue;                                             // uniform across the warp
+            bool emit = false; float3 sdir = f3(0, 0, 1), c = f3(0, 0, 0); float len = 3.402823466e+38f;
+            if (hit) {
+                const float3 lpos = f3(L.pos[0], L.pos[1], L.pos[2]), ldir = f3(L.dir[0], L.dir[1], L.dir[2]);
+                const float3 dtl = L.type == 0 ? norm3(-ldir) : norm3(lpos - hit_point);
+                const float dot_light = fmaxf(dot3(surface_normal, dtl), 0.0f);
+                const float3 mi = -dtl;
+                const float3 reflect_dir = mi - (2.0f * dot3(surface_normal, mi)) * surface_normal;
+                const float3 view_dir = norm3(-d);
+                const float spec_dot = fmaxf(dot3(reflect_dir, view_dir), 0.0f);
+                const float light_power = powf(spec_dot, shininess);
+                float intensity;
+                if (L.type == 0) intensity = L.intensity;
+                else {
+                    const float r2 = len3(lpos - hit_point);
+                    intensity = L.intensity / (4.0f * PI * r2);
+                    len = r2;
+                    if (L.type == 2) {
+                        const float dl = dot3(-dtl, norm3(ldir));
+                        if (acosf(dl) > L.max_angle) intensity = 0.0f;
+                    }
+                }
+                c = f3((L.color[0] * (specular_color.x * light_power + base_color.x * dot_light)) * intensity,
+                       (L.color[1] * (specular_color.y * light_power + base_color.y * dot_light)) * intensity,
+                       (L.color[2] * (specular_color.z * light_power + base_color.z * dot_light)) * intensity);
+                c = c * coef_d;
+                if (recv_shadow) {
+                    emit = true;
+                    sdir = dtl;
+                    if (F.monte_carlo && mat_mc) sdir = jitter(sdir, shadow_softness, F.mc_seed, pixel, sample, path, 2 + 2 * li);
+                } else direct = direct + c;
+            }
+            const uint32_t slot = queue_append(out.shadow_count, emit);
+            if (emit) {
+                if (slot < out.shadow_cap) {
+                    const float3 so = hit_point + surface_normal * 0.001f;
+                    out.shadow.o[slot] = make_float4(so.x, so.y, so.z, len);
+                    out.shadow.d[slot] = make_float4(sdir.x, sdir.y, sdir.z, __uint_as_float(pixel));
+                    out.shadow.c[slot] = make_float4(c.x, c.y, c.z, mat_alpha);
+                    out.shadow.r[slot] = h.item;
+                } else *out.overflow = 1u;
+            }
+        }
+        if (hit) {
+            const float3 acc = direct + constant;
+            if (acc.x != 0.0f || acc.y != 0.0f || acc.z != 0.0f) atomicAdd(&F.accum_c[pixel], make_float4(acc.x, acc.y, acc.z, 0.0f));
+        }
+        // --- child rays ---
+        {
+            const uint32_t slot = queue_append(out.child_count, emit_refl);
+            if (emit_refl) {
+                if (slot < out.child_cap) {
+                    const float3 nd = xnormalize(refl_d);                         // :722-723 of the recursive call
+                    out.child.o[slot] = make_float4(refl_o.x, refl_o.y, refl_o.z, w_refl);
+                    out.child.d[slot] = make_float4(nd.x, nd.y, nd.z, __uint_as_float(pixel));
+                    out.child.m[slot] = make_uint2(sample | ((depth + 1) << 16), path * 2u);
+                } else *out.overflow = 1u;
+            }
+        }
+        {
+            const uint32_t slot = queue_append(out.child_count, emit_trans);
+            if (emit_trans) {
+                if (slot < out.child_cap) {
+                    const float3 nd = xnormalize(trans_d);
+                    out.child.o[slot] = make_float4(trans_o.x, trans_o.y, trans_o.z, w_trans);
+                    out.child.d[slot] = make_float4(nd.x, nd.y, nd.z, __uint_as_float(pixel));
+                    out.child.m[slot] = make_uint2(sample | ((depth + 1) << 16) | (trans_flags << 24), path * 2u + 1u);
+                } else *out.overflow = 1u;
+            }
+        }
+    }
+}
+
+// ---- K6 ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) resolve_kernel(FrameDev F, const uint32_t* __restrict__ pixel_list, uint32_t n_pix,
+                                                      uchar4* __restrict__ rgba, float* __restrict__ normals, float* __restrict__ depth,
+                                                      uint32_t* __restrict__ object_ids) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pix; i += gridDim.x * blockDim.x) {
+        const uint32_t p = __ldg(pixel_list + i);
+        const float4 c = F.accum_c[p], nn = F.accum_n[p];
+        const float ns = (float)F.n_samples;
+        float r = fminf(xd(c.x, ns), 1.0f), g = fminf(xd(c.y, ns), 1.0f), b = fminf(xd(c.z, ns), 1.0f);   // :406-413
+        uchar4 px;
+        if (F.gamma) {
+            const float ge = 1.0f / 2.2f;
+            px = make_uchar4((unsigned char)as_u8(powf(r, ge) * 255.0f), (unsigned char)as_u8(powf(g, ge) * 255.0f),
+                             (unsigned char)as_u8(powf(b, ge) * 255.0f), 255);
+        } else px = make_uchar4((unsigned char)as_u8(xm(r, 255.0f)), (unsigned char)as_u8(xm(g, 255.0f)), (unsigned char)as_u8(xm(b, 255.0f)), 255);
+        if (rgba) rgba[p] = px;
+        if (normals) {
+            const float3 n = xnormalize(f3(xd(nn.x, ns), xd(nn.y, ns), xd(nn.z, ns)));       // NaN on a miss, like the reference
+            normals[3 * (size_t)p] = n.x; normals[3 * (size_t)p + 1] = n.y; normals[3 * (size_t)p + 2] = n.z;
+        }
+        if (depth) depth[p] = xd(c.w, ns);
+        if (object_ids) object_ids[p] = F.ids[p];
+    }
+}
+
+__global__ void clear_pixels_kernel(FrameDev F, const uint32_t* __restrict__ pixel_list, uint32_t n_pix) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pix; i += gridDim.x * blockDim.x) {
+        const uint32_t p = __ldg(pixel_list + i);
+        F.accum_c[p] = make_float4(0, 0, 0, 0); F.accum_n[p] = make_float4(0, 0, 0, 0); F.ids[p] = 0u;
+    }
+}
+
+// ---- probe ---------------------------------------------------------------------------------------
+struct ProbeRay { float o[3], d[3]; };
+struct ProbeHit { float t; float n[3]; uint32_t item_id, face_id; int32_t item_index; uint32_t reserved; };
+
+__global__ void probe_kernel(SceneDev S, const ProbeRay* __restrict__ rays, uint32_t n, int for_shadow, int stop_first, uint32_t depth,
+                             ProbeHit* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float3 o = f3(rays[i].o[0], rays[i].o[1], rays[i].o[2]), d = f3(rays[i].d[0], rays[i].d[1], rays[i].d[2]);
+    Best b; TravStats st{0, 0}; uint32_t a = 0, c = 0;
+    if (stop_first && for_shadow) trace_shadow_ordered<false>(S, o, d, depth, b, st);
+    else if (stop_first) {
+        // stop_on_first_hit without for_shadow is never issued by the reference; same ordered walk, solid rules of a camera ray
+        trace_closest<false>(S, o, d, false, depth, b, st, a, c);
+    } else trace_closest<false>(S, o, d, for_shadow != 0, depth, b, st, a, c);
+    ProbeHit h; h.reserved = 0;
+    if (b.item == 0xFFFFFFFFu) { h.t = -1.0f; h.n[0] = h.n[1] = h.n[2] = 0.0f; h.item_id = 0; h.face_id = 0; h.item_index = -1; }
+    else {
+        const DItem& it = S.items[b.item];
+        uint32_t face_id;
+        const float3 nn = hit_normal(S, it, o, d, b.t, b.prim, b.flags, face_id);
+        h.t = b.t; h.n[0] = nn.x; h.n[1] = nn.y; h.n[2] = nn.z; h.item_id = it.id; h.face_id = face_id; h.item_index = (int32_t)b.item;
+    }
+    out[i] = h;
+}
+
+// ---- shard pack / unpack ---------------------------------------------------------------------------
+__global__ void pack_kernel(const uint32_t* __restrict__ pixel_list, uint32_t n, const uchar4* rgba, const float* normals, const float* depth,
+                            const uint32_t* ids, uchar4* p_rgba, float* p_normals, float* p_depth, uint32_t* p_ids) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t p = __ldg(pixel_list + i);
+        p_rgba[i] = rgba[p];
+        p_normals[3 * (size_t)i] = normals[3 * (size_t)p]; p_normals[3 * (size_t)i + 1] = normals[3 * (size_t)p + 1]; p_normals[3 * (size_t)i + 2] = normals[3 * (size_t)p + 2];
+        p_depth[i] = depth[p]; p_ids[i] = ids[p];
+    }
+}
+__global__ void unpack_kernel(const uint32_t* __restrict__ pixel_list, uint32_t n, const uchar4* p_rgba, const float* p_normals, const float* p_depth,
+                              const uint32_t* p_ids, uchar4* rgba, float* normals, float* depth, uint32_t* ids) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t p = __ldg(pixel_list + i);
+        rgba[p] = p_rgba[i];
+        normals[3 * (size_t)p] = p_normals[3 * (size_t)i]; normals[3 * (size_t)p + 1] = p_normals[3 * (size_t)i + 1]; normals[3 * (size_t)p + 2] = p_normals[3 * (size_t)i + 2];
+        depth[p] = p_depth[i]; ids[p] = p_ids[i];
+    }
+}
+
+}  // namespace rtx
