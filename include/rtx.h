@@ -156,12 +156,15 @@ typedef struct RtxShard {
 typedef struct RtxStats {
     uint64_t rays_closest, rays_shadow;
     uint64_t primary_samples;
-    uint64_t node_visits, tri_tests, sphere_tests, item_tests;  /* only with RTX_DEBUG_COLLECT_STATS */
+    /* traversal work, [0] = closest-hit kernel, [1] = shadow kernel; only with RTX_DEBUG_COLLECT_STATS */
+    uint64_t node_visits[2], tri_tests[2];
+    uint64_t sphere_tests, item_tests;
     uint64_t kernel_launches;
     uint32_t waves, batches;
-    float device_ms;       /* CUDA events around all device work of the frame            */
-    float trace_ms;        /* CUDA events, closest-hit + shadow traversal kernels only    */
-    float shade_ms;        /* CUDA events, raygen + shade + resolve kernels               */
+    float device_ms;       /* CUDA events around all device work of the frame                      */
+    float closest_ms;      /* CUDA events, sum over closest-hit kernel launches                     */
+    float shadow_ms;       /* CUDA events, sum over shadow kernel launches                          */
+    float shade_ms;        /* device_ms - closest_ms - shadow_ms (raygen, shade, resolve, gaps)     */
     uint64_t h2d_bytes, d2h_bytes;
 } RtxStats;
 

@@ -307,12 +307,15 @@ void build_bvh2(Mesh& m) {
     }
 }
 
-// conservative slab test (tmax padded by 1+2*gamma(3), pbrt) so pruning never drops a real hit
+// conservative slab test.  The triangle toi (Ericson form) and the slab distances are rounded differently, so a
+// box is only skipped when it lies beyond the best toi by more than a 1e-5 relative margin on both ends:
+// pruning may never drop a hit the brute-force loop would keep (tests: BVH == brute force, bit for bit).
 inline bool box_hit(const Bvh2Node& n, const float o[3], const float inv[3], float tbest) {
     float t0 = 0.0f, t1 = tbest;
     for (int k = 0; k < 3; k++) {
         float a = (n.lo[k] - o[k]) * inv[k], b = (n.hi[k] - o[k]) * inv[k];
-        float tn = rmin(a, b), tf = rmax(a, b) * 1.0000004f;
+        float tn = rmin(a, b), tf = rmax(a, b);
+        tn = tn - std::fabs(tn) * 1e-5f; tf = tf + std::fabs(tf) * 1e-5f;
         t0 = rmax(t0, tn); t1 = rmin(t1, tf);
     }
     return t0 <= t1;

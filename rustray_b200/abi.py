@@ -75,14 +75,14 @@ class RtxShard(C.Structure):
 
 class RtxStats(C.Structure):
     _fields_ = [("rays_closest", C.c_uint64), ("rays_shadow", C.c_uint64), ("primary_samples", C.c_uint64),
-                ("node_visits", C.c_uint64), ("tri_tests", C.c_uint64), ("sphere_tests", C.c_uint64),
+                ("node_visits", C.c_uint64 * 2), ("tri_tests", C.c_uint64 * 2), ("sphere_tests", C.c_uint64),
                 ("item_tests", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("waves", C.c_uint32), ("batches", C.c_uint32),
-                ("device_ms", C.c_float), ("trace_ms", C.c_float), ("shade_ms", C.c_float),
+                ("device_ms", C.c_float), ("closest_ms", C.c_float), ("shadow_ms", C.c_float), ("shade_ms", C.c_float),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
     def as_dict(self) -> dict:
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        return {k: (list(getattr(self, k)) if hasattr(getattr(self, k), '__len__') else getattr(self, k)) for k, _ in self._fields_}
 
 
 class RtxRay(C.Structure):

@@ -566,7 +566,6 @@ int rtx_render_frame_device(RtxScene* sc, const RtxCamera* cam, const RtxConfig*
         return sc->events[i];
     };
     size_t ev_next = 2;
-    float trace_ms = 0.f;
     CU(cudaEventRecord(get_event(0), st));
     CU(cudaMemsetAsync(sc->ctr_pool.p, 0, kCtrPool * 4, st));
     CU(cudaMemsetAsync(sc->overflow.p, 0, 4, st));
@@ -669,18 +668,16 @@ int rtx_render_frame_device(RtxScene* sc, const RtxCamera* cam, const RtxConfig*
             cudaEventElapsedTime(&a, sc->events[i], sc->events[i + 1]); cudaEventElapsedTime(&b, sc->events[i + 2], sc->events[i + 3]);
             tc += a; ts += b;
         }
-        trace_ms = tc + ts;
-        stats->device_ms = ms; stats->trace_ms = trace_ms; stats->shade_ms = ms - trace_ms;
+        stats->device_ms = ms; stats->closest_ms = tc; stats->shadow_ms = ts; stats->shade_ms = ms - tc - ts;
         stats->rays_closest = rays_closest; stats->rays_shadow = rays_shadow; stats->primary_samples = primary;
         stats->kernel_launches = launches; stats->waves = waves; stats->batches = batches;
         stats->h2d_bytes = h2d; stats->d2h_bytes = (uint64_t)waves * 16;
         if (want_stats) {
             Counters c; CU(cudaMemcpy(&c, sc->counters.p, sizeof(c), cudaMemcpyDeviceToHost));
-            stats->node_visits = c.node_visits; stats->tri_tests = c.tri_tests; stats->sphere_tests = c.sphere_tests; stats->item_tests = c.item_tests;
+            stats->node_visits[0] = c.node_visits[0]; stats->node_visits[1] = c.node_visits[1];
+            stats->tri_tests[0] = c.tri_tests[0]; stats->tri_tests[1] = c.tri_tests[1];
+            stats->sphere_tests = c.sphere_tests; stats->item_tests = c.item_tests;
         }
-        // closest / shadow split of trace_ms is exposed through the two reserved-for-later fields of the stats struct:
-        // trace_ms = closest + shadow; shade_ms = everything else on the device.
-        (void)tc; (void)ts;
     }
     return RTX_OK;
 }

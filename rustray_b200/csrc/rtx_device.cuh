@@ -77,7 +77,7 @@ enum : uint32_t { HF_BACK = 1u, HF_INSIDE = 2u, HF_NEGN = 4u };   // HF_NEGN: pa
 enum : uint32_t { RF_ID_OWNER = 1u };
 
 struct Counters {      // device counters, 64-bit
-    unsigned long long rays_closest, rays_shadow, node_visits, tri_tests, sphere_tests, item_tests;
+    unsigned long long node_visits[2], tri_tests[2], sphere_tests, item_tests;   // [0] closest kernel, [1] shadow kernel
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -233,10 +233,11 @@ __device__ __forceinline__ uint32_t node_test(const float4* __restrict__ nodes, 
     const float ay = __uint_as_float(((ew >> 8) & 0xffu) << 23) * r.idir.y;
     const float az = __uint_as_float(((ew >> 16) & 0xffu) << 23) * r.idir.z;
     const float bx = (n0.x - r.o.x) * r.idir.x, by = (n0.y - r.o.y) * r.idir.y, bz = (n0.z - r.o.z) * r.idir.z;
-    // conservative padding: rounding of q*a + b is bounded by ~ulp(|b| + 255|a|)
-    const float px = fmaf(fabsf(ax), 255.0f, fabsf(bx)) * 2.4e-7f;
-    const float py = fmaf(fabsf(ay), 255.0f, fabsf(by)) * 2.4e-7f;
-    const float pz = fmaf(fabsf(az), 255.0f, fabsf(bz)) * 2.4e-7f;
+    // conservative padding: rounding of q*a + b is bounded by ~ulp(|b| + 255|a|); the margin also covers the few-ulp
+    // gap between a triangle's toi (Ericson form) and the slab distance of its own box when tmax is a previous hit
+    const float px = fmaf(fabsf(ax), 255.0f, fabsf(bx)) * 2e-6f;
+    const float py = fmaf(fabsf(ay), 255.0f, fabsf(by)) * 2e-6f;
+    const float pz = fmaf(fabsf(az), 255.0f, fabsf(bz)) * 2e-6f;
     const float blx = bx - px, bhx = bx + px, bly = by - py, bhy = by + py, blz = bz - pz, bhz = bz + pz;
     uint32_t hitmask = 0;
 #pragma unroll

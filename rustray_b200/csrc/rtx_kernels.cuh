@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(kTraceBlock) closest_kernel(SceneDev S, RayQ q
         }
     }
     if (STATS) {
-        atomicAdd(&ctr->node_visits, (unsigned long long)st.nodes); atomicAdd(&ctr->tri_tests, (unsigned long long)st.tris);
+        atomicAdd(&ctr->node_visits[0], (unsigned long long)st.nodes); atomicAdd(&ctr->tri_tests[0], (unsigned long long)st.tris);
         atomicAdd(&ctr->item_tests, (unsigned long long)n_items); atomicAdd(&ctr->sphere_tests, (unsigned long long)n_sph);
     }
 }
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kTraceBlock) shadow_kernel(SceneDev S, FrameDe
             atomicAdd(&F.accum_c[pixel], make_float4(rc.x * k, rc.y * k, rc.z * k, 0.0f));
         }
     }
-    if (STATS) { atomicAdd(&ctr->node_visits, (unsigned long long)st.nodes); atomicAdd(&ctr->tri_tests, (unsigned long long)st.tris); }
+    if (STATS) { atomicAdd(&ctr->node_visits[1], (unsigned long long)st.nodes); atomicAdd(&ctr->tri_tests[1], (unsigned long long)st.tris); }
 }
 
 // ---- K4 ------------------------------------------------------------------------------------------

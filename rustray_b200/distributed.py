@@ -1,0 +1,122 @@
+"""Multi-GPU frames: interleaved image tiles, one process per GPU, one gather of the G-buffer.
+
+The reference has no distributed path (threads only).  Pixels are independent and the
+scene is read-only during a frame, so the path shards with no data-path collective: the flattened
+scene is replicated on every GPU, tile t (row-major tiles of tile_w x tile_h pixels) belongs to rank
+t % world, each rank renders and resolves its own pixels, and ONE gather per frame brings the packed
+24 B/pixel G-buffer (rgba8 | normal 3xf32 | depth f32 | id u32) to rank 0, which scatters it into the
+four frame buffers (`torch.distributed.gather` over NCCL on GPUs; the same host logic runs over gloo
+on CPU in the tests with a numpy pack/unpack).
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+
+from . import abi
+
+DEFAULT_TILE = (8, 4)     # one warp of primary rays per tile
+
+
+def shard_pixels(width: int, height: int, rank: int, world: int, tile_w: int = DEFAULT_TILE[0], tile_h: int = DEFAULT_TILE[1]) -> np.ndarray:
+    """Frame pixel indices (y*width+x) owned by `rank`, in the order the library renders and packs them
+    (must match get_pixel_list in csrc/rtx_api.cu)."""
+    tx, ty = (width + tile_w - 1) // tile_w, (height + tile_h - 1) // tile_h
+    t = np.arange(rank, tx * ty, world, dtype=np.int64)
+    x0, y0 = (t % tx) * tile_w, (t // tx) * tile_h
+    dy, dx = np.mgrid[0:tile_h, 0:tile_w]
+    x = x0[:, None] + dx.reshape(1, -1)
+    y = y0[:, None] + dy.reshape(1, -1)
+    ok = (x < width) & (y < height)
+    return (y * width + x)[ok].astype(np.uint32)
+
+
+def packed_bytes(n_pixels: int) -> int:
+    return 24 * n_pixels
+
+
+def pack_numpy(pixels: np.ndarray, image, normals, depth, objects) -> np.ndarray:
+    """CPU mirror of rtx_shard_pack: rgba[n] | normals[n*3] | depth[n] | ids[n] as one byte buffer."""
+    n = pixels.size
+    out = np.zeros(24 * n, dtype=np.uint8)
+    out[: 4 * n] = image.reshape(-1, 4)[pixels].reshape(-1)
+    out[4 * n: 16 * n] = normals.reshape(-1, 3)[pixels].astype(np.float32).view(np.uint8).reshape(-1)
+    out[16 * n: 20 * n] = depth.reshape(-1)[pixels].astype(np.float32).view(np.uint8).reshape(-1)
+    out[20 * n: 24 * n] = objects.reshape(-1)[pixels].astype(np.uint32).view(np.uint8).reshape(-1)
+    return out
+
+
+def unpack_numpy(pixels: np.ndarray, packed: np.ndarray, image, normals, depth, objects) -> None:
+    n = pixels.size
+    image.reshape(-1, 4)[pixels] = packed[: 4 * n].reshape(-1, 4)
+    normals.reshape(-1, 3)[pixels] = packed[4 * n: 16 * n].view(np.float32).reshape(-1, 3)
+    depth.reshape(-1)[pixels] = packed[16 * n: 20 * n].view(np.float32)
+    objects.reshape(-1)[pixels] = packed[20 * n: 24 * n].view(np.uint32)
+
+
+def gather_frame_cpu(rank: int, world: int, width: int, height: int, local_frame, tile=DEFAULT_TILE, group=None):
+    """gloo path used by the CPU tests: every rank packs its owned pixels from `local_frame`
+    (renderer.Frame with at least those pixels valid); rank 0 returns the assembled Frame."""
+    import torch
+    import torch.distributed as dist
+    from .renderer import Frame
+    mine = shard_pixels(width, height, rank, world, *tile)
+    buf = torch.from_numpy(pack_numpy(mine, local_frame.image, local_frame.normals, local_frame.depth, local_frame.objects))
+    sizes = [packed_bytes(shard_pixels(width, height, r, world, *tile).size) for r in range(world)]
+    pad = max(sizes)
+    send = torch.zeros(pad, dtype=torch.uint8)
+    send[: buf.numel()] = buf
+    recv = [torch.zeros(pad, dtype=torch.uint8) for _ in range(world)] if rank == 0 else None
+    dist.gather(send, recv, dst=0, group=group)
+    if rank != 0:
+        return None
+    out = Frame(width, height)
+    for r in range(world):
+        px = shard_pixels(width, height, r, world, *tile)
+        unpack_numpy(px, recv[r][: sizes[r]].numpy(), out.image, out.normals, out.depth, out.objects)
+    return out
+
+
+class ShardedRenderer:
+    """One rank of a multi-GPU render.  `rm` is this rank's RendererManager (scene replicated)."""
+
+    def __init__(self, rm, width: int, height: int, rank: int, world: int, tile=DEFAULT_TILE, device=None):
+        import torch
+        self.rm, self.w, self.h, self.rank, self.world, self.tile = rm, width, height, rank, world, tile
+        self.dev = device if device is not None else torch.device("cuda", rm.device)
+        self.shard = abi.RtxShard(rank, world, tile[0], tile[1])
+        n = width * height
+        self.rgba = torch.zeros(n * 4, dtype=torch.uint8, device=self.dev)
+        self.normals = torch.zeros(n * 3, dtype=torch.float32, device=self.dev)
+        self.depth = torch.zeros(n, dtype=torch.float32, device=self.dev)
+        self.ids = torch.zeros(n, dtype=torch.int32, device=self.dev)
+        lib = rm._lib
+        self.sizes = [int(lib.rtx_shard_packed_bytes(width, height, abi.RtxShard(r, world, tile[0], tile[1]))) for r in range(world)]
+        self.pad = (max(self.sizes) + 15) // 16 * 16
+        self.send = torch.zeros(self.pad, dtype=torch.uint8, device=self.dev)
+        self.recv = [torch.zeros(self.pad, dtype=torch.uint8, device=self.dev) for _ in range(world)] if rank == 0 else None
+
+    def render_local(self, cam, cfg) -> abi.RtxStats:
+        import torch
+        stream = torch.cuda.current_stream(self.dev).cuda_stream
+        return self.rm.render_device(cam, cfg, self.shard, self.rgba, self.normals, self.depth, self.ids, stream)
+
+    def gather(self, group=None) -> None:
+        """Pack owned pixels, gather to rank 0, scatter into rank 0's frame buffers."""
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        lib = self.rm._lib
+        stream = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        rc = lib.rtx_shard_pack(self.w, self.h, C.byref(self.shard), self.rgba.data_ptr(), self.normals.data_ptr(), self.depth.data_ptr(),
+                                self.ids.data_ptr(), self.send.data_ptr(), stream)
+        self.rm._check(rc)
+        if self.world > 1:
+            dist.gather(self.send, self.recv, dst=0, group=group)
+            if self.rank == 0:
+                for r in range(1, self.world):
+                    sh = abi.RtxShard(r, self.world, self.tile[0], self.tile[1])
+                    rc = lib.rtx_shard_unpack(self.w, self.h, C.byref(sh), self.recv[r].data_ptr(), self.rgba.data_ptr(),
+                                              self.normals.data_ptr(), self.depth.data_ptr(), self.ids.data_ptr(), stream)
+                    self.rm._check(rc)

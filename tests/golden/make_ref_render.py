@@ -1,0 +1,16 @@
+"""Downsample the author's rendering of config 2 (a real output of the reference) into a small fixture.
+    python tests/golden/make_ref_render.py [/root/reference]"""
+import os
+import sys
+
+import numpy as np
+from PIL import Image
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ref = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+src = os.path.join(ref, "data", "renderings", "output_2022-5-16_20-47-31_00000000.png")
+im = np.asarray(Image.open(src).convert("RGB")).astype(np.float32)
+assert im.shape == (720, 1280, 3)
+small = im.reshape(180, 4, 320, 4, 3).mean(axis=(1, 3))
+Image.fromarray(np.clip(small + 0.5, 0, 255).astype(np.uint8)).save(os.path.join(HERE, "ref_render_c2_320x180.png"))
+print("wrote ref_render_c2_320x180.png")

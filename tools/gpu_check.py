@@ -48,6 +48,6 @@ for i in range(3):
     t = time.time(); f = rm.start(cam, cfg); dt = time.time() - t
     s = f.stats
     print("C2 full: wall %.3fs device %.1f ms trace %.1f ms rays %d+%d => %.1f Mrays/s (device), waves %d launches %d" % (
-        dt, s.device_ms, s.trace_ms, s.rays_closest, s.rays_shadow, (s.rays_closest + s.rays_shadow) / s.device_ms / 1e3, s.waves, s.kernel_launches))
+        dt, s.device_ms, s.closest_ms + s.shadow_ms, s.rays_closest, s.rays_shadow, (s.rays_closest + s.rays_shadow) / s.device_ms / 1e3, s.waves, s.kernel_launches))
 from PIL import Image
 Image.fromarray(f.image).save("gpurun_out/c2_gpu.png")
