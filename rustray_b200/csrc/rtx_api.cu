@@ -42,8 +42,7 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
         }                                                                                          \
     } while (0)
 
-constexpr uint32_t kLinearItems = 16;     // item loop instead of a TLAS up to this many items
-constexpr uint32_t kCtrPool = 1u << 16;   // counters (4 per wave) zeroed in one memset
+constexpr uint32_t kCtrPool = 1u << 17;   // counters (8 per wave) zeroed in one memset
 
 inline bool approx_equal_h(float a, float b) { return std::trunc(a * 1000000.0f) == std::trunc(b * 1000000.0f); }
 
@@ -90,11 +89,11 @@ struct RtxScene {
     // queues
     uint32_t chunk = 0, levels = 0, level_cap = 0, shadow_cap = 0;
     DevBuf<float4> q_o, q_d; DevBuf<uint2> q_m;
-    DevBuf<float4> s_o, s_d, s_c; DevBuf<uint32_t> s_r;
+    DevBuf<float4> s_o, s_d, s_c; DevBuf<uint32_t> s_r, s_slow;
     DevBuf<HitRec> hits; DevBuf<uint32_t> ctr_pool; DevBuf<uint32_t> overflow; DevBuf<Counters> counters;
     uint32_t* h_ctr = nullptr;              // pinned, 4 uint32
     std::vector<cudaEvent_t> events;
-    int blocks_closest = 0, blocks_closest_st = 0, blocks_shadow = 0, blocks_shadow_st = 0, blocks_shadow_ord = 0;
+    int blocks_closest = 0, blocks_closest_st = 0, blocks_shadow = 0, blocks_shadow_st = 0;
     // host-output staging for rtx_render_frame
     DevBuf<uchar4> o_rgba; DevBuf<float> o_normals, o_depth; DevBuf<uint32_t> o_ids;
     // probe staging
@@ -157,7 +156,7 @@ int build_tlas(RtxScene& sc, std::vector<float4>& tlas_nodes, std::vector<uint32
     std::vector<Aabb3> boxes(sc.h_items.size());
     for (size_t i = 0; i < sc.h_items.size(); i++) item_world_box(sc.h_items[i], boxes[i]);
     WideBvh bvh; build_wide_bvh(boxes.data(), (uint32_t)boxes.size(), bvh);
-    if (bvh.max_depth > 14) return fail(RTX_E_INVALID, "TLAS too deep");
+    if (bvh.max_depth > 6) return fail(RTX_E_INVALID, "TLAS too deep for the traversal stack");
     tlas_nodes.clear();
     append_nodes(tlas_nodes, bvh, sc.n_blas_nodes, 0);
     tlas_prims = bvh.prim_order;
@@ -181,8 +180,12 @@ void refresh_dev(RtxScene& sc) {
     D.verts = sc.verts.p; D.idx = sc.idx.p; D.uvs = sc.uvs.p; D.uv_idx = sc.uv_idx.p; D.nrms = sc.nrms.p; D.n_idx = sc.n_idx.p;
     D.mats = sc.mats.p; D.texs = sc.texs.p; D.texels = sc.texels.p; D.lights = sc.lights.p;
     D.n_items = (uint32_t)sc.h_items.size();
-    D.tlas_root = sc.n_blas_nodes; D.use_tlas = sc.h_items.size() > kLinearItems ? 1u : 0u;
+    D.tlas_root = sc.n_blas_nodes; D.use_tlas = 1u;
     D.ball_flip_inside = 1u;
+    if (!sc.overflow.p) sc.overflow.alloc(4);
+    D.dbg = sc.overflow.p + 1;
+    D.any_alpha_tex = 0u;
+    for (const DItem& it : sc.h_items) if (it.flags & IF_ALPHA_TEX) D.any_alpha_tex = 1u;
 }
 
 int get_pixel_list(RtxScene& sc, uint32_t w, uint32_t h, const RtxShard* shard, PixelList** out) {
@@ -267,8 +270,8 @@ int ensure_queues(RtxScene& sc, uint32_t max_recursion, uint32_t n_lights_enable
     size_t qn = (size_t)sc.levels * sc.level_cap;
     int rc;
     if ((rc = sc.q_o.alloc(qn)) || (rc = sc.q_d.alloc(qn)) || (rc = sc.q_m.alloc(qn))) return rc;
-    if ((rc = sc.s_o.alloc(sc.shadow_cap)) || (rc = sc.s_d.alloc(sc.shadow_cap)) || (rc = sc.s_c.alloc(sc.shadow_cap)) || (rc = sc.s_r.alloc(sc.shadow_cap))) return rc;
-    if ((rc = sc.hits.alloc(chunk)) || (rc = sc.ctr_pool.alloc(kCtrPool)) || (rc = sc.overflow.alloc(1)) || (rc = sc.counters.alloc(1))) return rc;
+    if ((rc = sc.s_o.alloc(sc.shadow_cap)) || (rc = sc.s_d.alloc(sc.shadow_cap)) || (rc = sc.s_c.alloc(sc.shadow_cap)) || (rc = sc.s_r.alloc(sc.shadow_cap)) || (rc = sc.s_slow.alloc(sc.shadow_cap))) return rc;
+    if ((rc = sc.hits.alloc(chunk)) || (rc = sc.ctr_pool.alloc(kCtrPool)) || (rc = sc.overflow.alloc(4)) || (rc = sc.counters.alloc(1))) return rc;
     if (!sc.h_ctr) CU(cudaMallocHost(&sc.h_ctr, 16));
     return RTX_OK;
 }
@@ -278,9 +281,8 @@ int occupancy_blocks(RtxScene& sc) {
     int b = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, closest_kernel<false>, kTraceBlock, 0)); sc.blocks_closest = std::max(1, b) * sc.sm_count;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, closest_kernel<true>, kTraceBlock, 0)); sc.blocks_closest_st = std::max(1, b) * sc.sm_count;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, shadow_kernel<false, false>, kTraceBlock, 0)); sc.blocks_shadow = std::max(1, b) * sc.sm_count;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, shadow_kernel<true, false>, kTraceBlock, 0)); sc.blocks_shadow_st = std::max(1, b) * sc.sm_count;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, shadow_kernel<false, true>, kTraceBlock, 0)); sc.blocks_shadow_ord = std::max(1, b) * sc.sm_count;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, shadow_any_kernel<false>, kTraceBlock, 0)); sc.blocks_shadow = std::max(1, b) * sc.sm_count;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, shadow_any_kernel<true>, kTraceBlock, 0)); sc.blocks_shadow_st = std::max(1, b) * sc.sm_count;
     return RTX_OK;
 }
 
@@ -372,7 +374,7 @@ int rtx_scene_create(const RtxSceneDesc* d, int device, RtxScene** out) {
             for (int k = 0; k < 3; k++) { o.lo[k] = std::min(o.lo[k], b.lo[k]); o.hi[k] = std::max(o.hi[k], b.hi[k]); }   // TriMesh::aabb
         }
         WideBvh bvh; build_wide_bvh(boxes.data(), m.n_faces, bvh);
-        if (bvh.max_depth >= kStack - 2) return bail(RTX_E_INVALID, "BLAS too deep for the traversal stack");
+        if (bvh.max_depth >= kStack - 2 || 2 * bvh.max_depth + 2 * 6 + 4 > kLaneStack) return bail(RTX_E_INVALID, "BLAS too deep for the traversal stack");
         const uint32_t node_off = (uint32_t)(h_nodes.size() / 5), tri_off = (uint32_t)(h_tris.size() / 3);
         sc->mesh_root[mi] = node_off;
         append_nodes(h_nodes, bvh, node_off, tri_off);
@@ -409,7 +411,7 @@ int rtx_scene_create(const RtxSceneDesc* d, int device, RtxScene** out) {
     // ---- TLAS (only used above kLinearItems; space reserved for updates) ----
     std::vector<float4> tlas_nodes; std::vector<uint32_t> tlas_prims;
     sc->tlas_cap = std::max<uint32_t>(8, d->n_items);
-    if (d->n_items > kLinearItems) { int rc = build_tlas(*sc, tlas_nodes, tlas_prims); if (rc) { rtx_scene_destroy(sc); return rc; } }
+    if (d->n_items > 0) { int rc = build_tlas(*sc, tlas_nodes, tlas_prims); if (rc) { rtx_scene_destroy(sc); return rc; } }
     h_nodes.insert(h_nodes.end(), tlas_nodes.begin(), tlas_nodes.end());
     h_nodes.resize(((size_t)sc->n_blas_nodes + sc->tlas_cap) * 5, make_float4(0, 0, 0, 0));
     tlas_prims.resize(std::max<size_t>(1, d->n_items), 0);
@@ -463,7 +465,7 @@ int rtx_scene_destroy(RtxScene* sc) {
     sc->verts.release(); sc->uvs.release(); sc->nrms.release(); sc->idx.release(); sc->uv_idx.release(); sc->n_idx.release();
     sc->mats.release(); sc->texs.release(); sc->texels.release(); sc->lights.release();
     sc->accum_c.release(); sc->accum_n.release(); sc->ids.release(); sc->sample_table.release();
-    sc->q_o.release(); sc->q_d.release(); sc->q_m.release(); sc->s_o.release(); sc->s_d.release(); sc->s_c.release(); sc->s_r.release();
+    sc->q_o.release(); sc->q_d.release(); sc->q_m.release(); sc->s_o.release(); sc->s_d.release(); sc->s_c.release(); sc->s_r.release(); sc->s_slow.release();
     sc->hits.release(); sc->ctr_pool.release(); sc->overflow.release(); sc->counters.release();
     sc->o_rgba.release(); sc->o_normals.release(); sc->o_depth.release(); sc->o_ids.release(); sc->p_rays.release(); sc->p_hits.release();
     for (auto& kv : sc->pixel_lists) { kv.second->d.release(); delete kv.second; }
@@ -491,7 +493,7 @@ int rtx_scene_update_items(RtxScene* sc, const RtxItemXform* x, size_t n) {
     }
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(sc->items.p, sc->h_items.data(), sc->h_items.size() * sizeof(DItem), cudaMemcpyHostToDevice));
-    if (sc->h_items.size() > kLinearItems) {                              // Scene::update rebuilds the item BVH (scene.rs:1681-1687)
+    if (!sc->h_items.empty()) {                                           // Scene::update rebuilds the item BVH (scene.rs:1681-1687)
         std::vector<float4> tn; std::vector<uint32_t> tp;
         int rc = build_tlas(*sc, tn, tp); if (rc) return rc;
         if (tn.size() / 5 > sc->tlas_cap) return fail(RTX_E_INVALID, "TLAS capacity exceeded");
@@ -568,7 +570,7 @@ int rtx_render_frame_device(RtxScene* sc, const RtxCamera* cam, const RtxConfig*
     size_t ev_next = 2;
     CU(cudaEventRecord(get_event(0), st));
     CU(cudaMemsetAsync(sc->ctr_pool.p, 0, kCtrPool * 4, st));
-    CU(cudaMemsetAsync(sc->overflow.p, 0, 4, st));
+    CU(cudaMemsetAsync(sc->overflow.p, 0, 16, st));
     if (want_stats) CU(cudaMemsetAsync(sc->counters.p, 0, sizeof(Counters), st));
     uint64_t launches = 0;
     const int gs = sc->sm_count * 8;
@@ -607,14 +609,15 @@ int rtx_render_frame_device(RtxScene* sc, const RtxCamera* cam, const RtxConfig*
         const uint32_t n = std::min(counts[d], chunk);
         const uint32_t q_base = counts[d] - n;
         counts[d] -= n;
-        if (ctr_idx + 4 > kCtrPool) {                                    // stream is idle here (we sync every wave)
+        if (ctr_idx + 8 > kCtrPool) {                                    // stream is idle here (we sync every wave)
             CU(cudaMemsetAsync(sc->ctr_pool.p, 0, kCtrPool * 4, st)); ctr_idx = 0;
         }
-        uint32_t* ctr = sc->ctr_pool.p + ctr_idx; ctr_idx += 4;          // [0] closest work, [1] shadow work, [2] child count, [3] shadow count
+        uint32_t* ctr = sc->ctr_pool.p + ctr_idx; ctr_idx += 8;          // [0] closest work, [1] shadow work, [2] child count, [3] shadow count, [4] slow count
         RayQ Q = level_queue(*sc, d);
         const uint32_t warps = (n + 31) / 32;
         cudaEvent_t e0 = get_event(ev_next), e1 = get_event(ev_next + 1), e2 = get_event(ev_next + 2), e3 = get_event(ev_next + 3);
         ev_next += 4;
+        if (getenv("RTX_VERIFY")) cudaMemsetAsync(sc->hits.p, 0xEE, (size_t)n * sizeof(HitRec), st);
         CU(cudaEventRecord(e0, st));
         {
             const int maxb = want_stats ? sc->blocks_closest_st : sc->blocks_closest;
@@ -624,6 +627,23 @@ int rtx_render_frame_device(RtxScene* sc, const RtxCamera* cam, const RtxConfig*
             launches++;
         }
         CU(cudaEventRecord(e1, st));
+        if (getenv("RTX_VERIFY")) {
+            static uint32_t* d_cnt = nullptr; static VerifyRec* d_rec = nullptr;
+            if (!d_cnt) { cudaMalloc(&d_cnt, 4); cudaMalloc(&d_rec, 64 * sizeof(VerifyRec)); }
+            cudaMemsetAsync(d_cnt, 0, 4, st);
+            verify_closest_kernel<<<(n + 127) / 128, 128, 0, st>>>(sc->dev, Q, q_base, n, sc->hits.p, d_cnt, d_rec, 64);
+            uint32_t hc = 0; VerifyRec hr[64];
+            cudaMemcpyAsync(&hc, d_cnt, 4, cudaMemcpyDeviceToHost, st); cudaStreamSynchronize(st);
+            if (hc) {
+                cudaMemcpy(hr, d_rec, sizeof(hr), cudaMemcpyDeviceToHost);
+                uint32_t ovf[4]; cudaMemcpy(ovf, sc->overflow.p, 16, cudaMemcpyDeviceToHost);
+                fprintf(stderr, "[RTX_VERIFY] wave %u depth %u n %u: %u mismatching closest hits (queue overflow %u, lane stack overflow %u) err=%s\n", waves, d, n, hc, ovf[0], ovf[1], cudaGetErrorString(cudaGetLastError()));
+                for (uint32_t k = 0; k < std::min(hc, 40u); k++)
+                    fprintf(stderr, "   idx %u o %.9g %.9g %.9g d %.9g %.9g %.9g depth %u | prod t %.9g item %x prim %u | ref t %.9g item %d prim %u\n", hr[k].index, hr[k].o[0], hr[k].o[1],
+                            hr[k].o[2], hr[k].d[0], hr[k].d[1], hr[k].d[2], hr[k].depth, hr[k].t_prod, (int)hr[k].item_prod, hr[k].prim_prod, hr[k].t_ref,
+                            (int)hr[k].item_ref, hr[k].prim_ref);
+            }
+        }
         {
             ShadeOut so;
             const uint32_t nd = d + 1 <= L ? d + 1 : d;                  // depth L never spawns children (depth <= max_recursion fails)
@@ -639,10 +659,17 @@ int rtx_render_frame_device(RtxScene* sc, const RtxCamera* cam, const RtxConfig*
         }
         CU(cudaEventRecord(e2, st));
         if (n_enabled > 0) {
-            if (ordered) shadow_kernel<false, true><<<sc->blocks_shadow_ord, kTraceBlock, 0, st>>>(sc->dev, F, SQ, ctr + 3, d, ctr + 1, sc->counters.p);
-            else if (want_stats) shadow_kernel<true, false><<<sc->blocks_shadow_st, kTraceBlock, 0, st>>>(sc->dev, F, SQ, ctr + 3, d, ctr + 1, sc->counters.p);
-            else shadow_kernel<false, false><<<sc->blocks_shadow, kTraceBlock, 0, st>>>(sc->dev, F, SQ, ctr + 3, d, ctr + 1, sc->counters.p);
-            launches++;
+            const int eb = sc->sm_count * 8;
+            if (ordered) {
+                shadow_exact_kernel<false, true><<<eb, kTraceBlock, 0, st>>>(sc->dev, F, SQ, nullptr, ctr + 3, d, sc->counters.p);
+                launches++;
+            } else {
+                if (want_stats) shadow_any_kernel<true><<<sc->blocks_shadow_st, kTraceBlock, 0, st>>>(sc->dev, F, SQ, ctr + 3, d, ctr + 1, sc->s_slow.p, ctr + 4, sc->counters.p);
+                else shadow_any_kernel<false><<<sc->blocks_shadow, kTraceBlock, 0, st>>>(sc->dev, F, SQ, ctr + 3, d, ctr + 1, sc->s_slow.p, ctr + 4, sc->counters.p);
+                if (want_stats) shadow_exact_kernel<true, false><<<eb, kTraceBlock, 0, st>>>(sc->dev, F, SQ, sc->s_slow.p, ctr + 4, d, sc->counters.p);
+                else shadow_exact_kernel<false, false><<<eb, kTraceBlock, 0, st>>>(sc->dev, F, SQ, sc->s_slow.p, ctr + 4, d, sc->counters.p);
+                launches += 2;
+            }
         }
         CU(cudaEventRecord(e3, st));
         CU(cudaMemcpyAsync(sc->h_ctr, ctr, 16, cudaMemcpyDeviceToHost, st));
@@ -710,7 +737,21 @@ int rtx_trace_probe(RtxScene* sc, const RtxRay* rays, size_t n, int for_shadow, 
     int rc;
     if ((rc = sc->p_rays.alloc(n)) || (rc = sc->p_hits.alloc(n))) return rc;
     CU(cudaMemcpy(sc->p_rays.p, rays, n * sizeof(RtxRay), cudaMemcpyHostToDevice));
-    probe_kernel<<<(unsigned)((n + 127) / 128), 128>>>(sc->dev, sc->p_rays.p, (uint32_t)n, for_shadow, stop_on_first_hit, depth, sc->p_hits.p);
+    if (!for_shadow && !stop_on_first_hit) {
+        // camera-type rays go through the PRODUCTION kernel (persistent closest_kernel), in chunks of the ray queue
+        if ((rc = ensure_queues(*sc, 6, 1)) || (rc = occupancy_blocks(*sc))) return rc;
+        RayQ Q = level_queue(*sc, 1);
+        for (size_t off = 0; off < n; off += sc->chunk) {
+            const uint32_t m = (uint32_t)std::min<size_t>(sc->chunk, n - off);
+            CU(cudaMemsetAsync(sc->ctr_pool.p, 0, 32, 0));
+            probe_pack_kernel<<<(m + 127) / 128, 128>>>(sc->p_rays.p + off, m, depth, Q);
+            const int blocks = (int)std::min<uint32_t>((m + kTraceBlock - 1) / kTraceBlock, (uint32_t)sc->blocks_closest);
+            closest_kernel<false><<<blocks, kTraceBlock>>>(sc->dev, Q, 0, m, sc->hits.p, sc->ctr_pool.p, sc->counters.p);
+            probe_unpack_kernel<<<(m + 127) / 128, 128>>>(sc->dev, sc->p_rays.p + off, sc->hits.p, m, sc->p_hits.p + off);
+        }
+    } else {
+        probe_kernel<<<(unsigned)((n + 127) / 128), 128>>>(sc->dev, sc->p_rays.p, (uint32_t)n, for_shadow, stop_on_first_hit, depth, sc->p_hits.p);
+    }
     CU(cudaGetLastError());
     CU(cudaMemcpy(hits, sc->p_hits.p, n * sizeof(RtxHit), cudaMemcpyDeviceToHost));
     return RTX_OK;

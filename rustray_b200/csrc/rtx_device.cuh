@@ -53,7 +53,8 @@ struct SceneDev {
     const float* verts; const uint32_t* idx; const float* uvs; const uint32_t* uv_idx; const float* nrms; const uint32_t* n_idx;
     const DMaterial* mats; const DTex* texs; const uchar4* texels; const DLight* lights;
     uint32_t n_items, n_lights, tlas_root, use_tlas;
-    uint32_t ball_flip_inside, pad[3];
+    uint32_t ball_flip_inside, any_alpha_tex, pad[2];
+    uint32_t* dbg;      // debug counters: [0] lane stack overflow
 };
 
 struct FrameDev {
@@ -205,18 +206,21 @@ __device__ __forceinline__ uint32_t bfind(uint32_t x) { return 31u - __clz(x); }
 
 struct TravStats { uint32_t nodes, tris; };
 struct MeshHit { float t; uint32_t prim, face, back; };
-enum { TM_CLOSEST = 0, TM_ANY_LE = 1, TM_ANY_GT = 2 };
+enum { TM_CLOSEST = 0, TM_ANY_LE = 1, TM_ANY_GT = 2, TM_CLASSIFY = 3 };
 constexpr int kStack = 28;
 
 struct WideRay {        // per-ray constants of the node test
     float3 o, d, idir; uint32_t octinv4;
 };
+__device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ WideRay make_wide_ray(float3 o, float3 d) {
     WideRay r; r.o = o; r.d = d;
     const float eps = 1e-20f;
-    r.idir.x = 1.0f / (fabsf(d.x) > eps ? d.x : copysignf(eps, d.x));
-    r.idir.y = 1.0f / (fabsf(d.y) > eps ? d.y : copysignf(eps, d.y));
-    r.idir.z = 1.0f / (fabsf(d.z) > eps ? d.z : copysignf(eps, d.z));
+    // a zero component (either sign) counts as positive, consistently with the near/far selection in node_test;
+    // the reciprocal only feeds the conservative (padded) box test, so MUFU.RCP accuracy is enough
+    r.idir.x = fast_rcp(fabsf(d.x) > eps ? d.x : (d.x < 0.0f ? -eps : eps));
+    r.idir.y = fast_rcp(fabsf(d.y) > eps ? d.y : (d.y < 0.0f ? -eps : eps));
+    r.idir.z = fast_rcp(fabsf(d.z) > eps ? d.z : (d.z < 0.0f ? -eps : eps));
     uint32_t oct = (d.x < 0.0f ? 4u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 1u : 0u);
     r.octinv4 = (7u - oct) * 0x01010101u;
     return r;
@@ -273,6 +277,8 @@ __device__ __forceinline__ uint32_t node_test(const float4* __restrict__ nodes, 
 //  TM_CLOSEST: mh = closest triangle with toi <= limit (ties: lowest face index); limit prunes.
 //  TM_ANY_LE : true as soon as a triangle with toi <= limit is found.
 //  TM_ANY_GT : true as soon as a triangle with toi >  limit is found.
+//  TM_CLASSIFY: true as soon as a triangle with toi <= limit is found; otherwise mh.back = 1 if any triangle
+//               was hit beyond limit (after the first such hit the search is clipped to [0, limit]).
 template <int MODE, bool STATS>
 __device__ __forceinline__ bool traverse_mesh(const float4* __restrict__ nodes, const float4* __restrict__ tris, uint32_t root,
                                               float3 o, float3 d, float limit, MeshHit& mh, TravStats& st) {
@@ -280,9 +286,10 @@ __device__ __forceinline__ bool traverse_mesh(const float4* __restrict__ nodes, 
     uint2 stack[kStack]; int sp = 0;
     uint2 ngroup = make_uint2(root, 0x80000000u), tgroup = make_uint2(0u, 0u);
     float tmin = (MODE == TM_ANY_GT) ? limit : 0.0f;
-    float tmax = (MODE == TM_ANY_GT) ? 3.402823466e+38f : limit;
+    float tmax = (MODE == TM_ANY_GT || MODE == TM_CLASSIFY) ? 3.402823466e+38f : limit;
     bool found = false;
     if (MODE == TM_CLOSEST) { mh.t = 3.402823466e+38f; mh.face = 0xFFFFFFFFu; }
+    if (MODE == TM_CLASSIFY) mh.back = 0u;
     for (;;) {
         if (ngroup.y > 0x00FFFFFFu) {
             const uint32_t hits = ngroup.y, imask = ngroup.y;
@@ -313,6 +320,9 @@ __device__ __forceinline__ bool traverse_mesh(const float4* __restrict__ nodes, 
                     }
                 } else if (MODE == TM_ANY_LE) {
                     if (toi <= limit) return true;
+                } else if (MODE == TM_CLASSIFY) {
+                    if (toi <= limit) return true;
+                    mh.back = 1u; tmax = limit;
                 } else {
                     if (toi > limit) return true;
                 }
@@ -504,11 +514,11 @@ __device__ __forceinline__ void trace_shadow_ordered(const SceneDev& S, float3 o
     }
 }
 
-// Equivalent two-phase any-hit walk used by the shadow kernel.  `len` = light distance (+inf for
-// directional).  Result: occluder item (or ~0u when lit).  When the occluder's material has an
-// alpha texture the closest hit on it is also returned (needed for the attenuation lookup).
-//   phase 1: first item k in order with a hit at toi <= len          -> candidate occluder
-//   phase 2: an earlier item j < k with a hit at all (so toi > len)   -> the reference stops at j: lit
+// Equivalent single-pass walk used by the shadow kernels.  `len` = light distance (+inf for directional).
+// Per candidate item, in order, ONE traversal classifies it: a hit at toi <= len (the item's closest hit is
+// then <= len: occluder, stop), only hits beyond len (the reference stops here with toi > len: lit), or no
+// hit (next item).  When the occluder's material has an alpha texture its closest hit is also returned
+// (needed for the attenuation lookup, raytracing.rs:898-912).
 template <bool STATS>
 __device__ __forceinline__ void trace_shadow_fast(const SceneDev& S, float3 o, float3 d, uint32_t depth, float len, Best& best, TravStats& st) {
     best.item = 0xFFFFFFFFu; best.t = 3.402823466e+38f; best.prim = 0; best.flags = 0; best.key = 0.0f;
@@ -517,28 +527,25 @@ __device__ __forceinline__ void trace_shadow_fast(const SceneDev& S, float3 o, f
     for (;;) {
         collect_candidates(S, o, d, depth, ckey, citem, have, cl);
         for (int k = 0; k < cl.n; k++) {
-            MeshHit mh; uint32_t hf = 0;
-            if (item_shadow_test<TM_ANY_LE, STATS>(S, cl.item[k], o, d, len, mh, hf, st)) {
-                // phase 2 over everything before (key, item) in order — only needed for finite len
-                if (len < 3.402823466e+38f) {
-                    const float kkey = cl.key[k]; const uint32_t kitem = cl.item[k];
-                    float c2 = 0.0f; uint32_t i2 = 0; bool h2 = false;
-                    CandList c;
-                    for (;;) {
-                        collect_candidates(S, o, d, depth, c2, i2, h2, c);
-                        bool done = false;
-                        for (int q = 0; q < c.n; q++) {
-                            if (!(c.key[q] < kkey || (c.key[q] == kkey && c.item[q] < kitem))) { done = true; break; }
-                            MeshHit m2; uint32_t f2;
-                            if (item_shadow_test<TM_ANY_GT, STATS>(S, c.item[q], o, d, len, m2, f2, st)) return;   // lit
-                        }
-                        if (done || !c.more || c.n == 0) break;
-                        c2 = c.key[c.n - 1]; i2 = c.item[c.n - 1]; h2 = true;
-                    }
-                }
-                best.item = cl.item[k]; best.key = cl.key[k]; best.t = 0.0f;
-                if (S.items[cl.item[k]].flags & IF_ALPHA_TEX) {
-                    item_shadow_test<TM_CLOSEST, STATS>(S, cl.item[k], o, d, 3.402823466e+38f, mh, hf, st);
+            const uint32_t ii = cl.item[k];
+            const DItem* it = S.items + ii;
+            float4 inv[3] = {__ldg(&it->inv[0]), __ldg(&it->inv[1]), __ldg(&it->inv[2])};
+            const float3 lo3 = xform_point(inv, o), ld3 = xform_vec(inv, d);
+            int cls;                                                   // 0 none, 1 hit <= len, 2 only beyond len
+            MeshHit mh;
+            if (it->flags & IF_MESH) {
+                const bool le = traverse_mesh<TM_CLASSIFY, STATS>(S.nodes, S.tris, it->root, lo3, ld3, len, mh, st);
+                cls = le ? 1 : (mh.back ? 2 : 0);
+            } else {
+                float t; bool inside;
+                cls = ball_cast(__ldg(&it->lo).w, lo3, ld3, false, t, inside) ? (t <= len ? 1 : 2) : 0;
+            }
+            if (cls == 2) return;                                      // first item hit at all lies beyond the light: lit
+            if (cls == 1) {
+                best.item = ii; best.key = cl.key[k]; best.t = 0.0f;
+                if (it->flags & IF_ALPHA_TEX) {
+                    uint32_t hf = 0;
+                    item_shadow_test<TM_CLOSEST, STATS>(S, ii, o, d, 3.402823466e+38f, mh, hf, st);
                     best.t = mh.t; best.prim = mh.prim; best.flags = hf;
                 }
                 return;
@@ -547,6 +554,133 @@ __device__ __forceinline__ void trace_shadow_fast(const SceneDev& S, float3 o, f
         if (!cl.more || cl.n == 0) return;
         ckey = cl.key[cl.n - 1]; citem = cl.item[cl.n - 1]; have = true;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// unified two-level traversal: ONE loop and ONE stack per lane (TLAS over items -> instance push ->
+// per-mesh BLAS -> instance pop), written as a resumable step so that a warp can refill finished
+// lanes with new rays (persistent threads with dynamic fetch).
+//   UT_CLOSEST : Raytracing::trace(.., stop_on_first_hit = false): global closest hit, reference order rule
+//   UT_ANY     : "is there any item with a hit at toi <= tmax" (order-independent half of the shadow query)
+// ------------------------------------------------------------------------------------------------
+enum { UT_CLOSEST = 0, UT_ANY = 1 };
+constexpr int kLaneStack = 48;
+
+struct Lane {
+    WideRay w;                  // world-space ray (o, d, 1/d, octant)
+    WideRay r;                  // ray of the current space (world in the TLAS, object space inside an item)
+    float tmax;                 // UT_CLOSEST: best toi so far (prunes); UT_ANY: light distance
+    uint2 ng, tg;               // pending node group / leaf group
+    int sp, blas_base;          // blas_base < 0: walking the TLAS
+    uint32_t cur_item; float cur_key;
+    float bkey; uint32_t bitem, bprim, bface, bflags;      // result (bitem = ~0u: none)
+};
+
+__device__ __forceinline__ void lane_init(Lane& L, const SceneDev& S, float3 o, float3 d, float tmax) {
+    L.w = make_wide_ray(o, d); L.r = L.w; L.tmax = tmax;
+    L.ng = make_uint2(S.tlas_root, 0x80000000u); L.tg = make_uint2(0u, 0u); L.sp = 0; L.blas_base = -1;
+    L.cur_item = 0; L.cur_key = 0.0f; L.bkey = 0.0f; L.bitem = 0xFFFFFFFFu; L.bprim = 0; L.bface = 0xFFFFFFFFu; L.bflags = 0;
+}
+
+// closest-hit merge with the reference's order rule (strictly smaller toi wins; equal toi: earlier in the
+// stable bbox-key sort, i.e. smaller (key, item index); inside one mesh: lowest face index)
+__device__ __forceinline__ void lane_accept(Lane& L, float toi, float key, uint32_t item, uint32_t prim, uint32_t face, uint32_t flags) {
+    bool take = toi < L.tmax;
+    if (!take && toi == L.tmax && L.bitem != 0xFFFFFFFFu)
+        take = key < L.bkey || (key == L.bkey && (item < L.bitem || (item == L.bitem && face < L.bface)));
+    if (take) { L.tmax = toi; L.bkey = key; L.bitem = item; L.bprim = prim; L.bface = face; L.bflags = flags; }
+}
+
+// The traversal is split into warp-synchronous phases (see the kernels): in a NODE phase every lane that has a
+// pending node group tests one node; in a LEAF phase every lane that has pending leaf entries handles exactly
+// one (a triangle, or an item of the TLAS).  Leaf entries are postponed — parked in `tg`, or on the stack when a
+// later node test produces more — until enough lanes of the warp have some, so triangle tests run on mostly
+// full warps instead of the 4-5 lanes that happen to reach a leaf in the same step.
+template <int MODE, bool STATS>
+__device__ __forceinline__ void lane_node(Lane& L, uint2* __restrict__ stack, const SceneDev& S, TravStats& st) {
+    if (L.sp + 2 > kLaneStack) { atomicAdd(S.dbg, 1u); return; }
+    if (L.tg.y != 0u) stack[L.sp++] = L.tg;                               // park postponed leaf entries
+    const uint32_t hits = L.ng.y, imask = L.ng.y;
+    const uint32_t cbit = bfind(hits);
+    const uint32_t base = L.ng.x;
+    L.ng.y &= ~(1u << cbit);
+    if (L.ng.y > 0x00FFFFFFu) stack[L.sp++] = L.ng;
+    const uint32_t slot = (cbit - 24u) ^ (L.r.octinv4 & 0xffu);
+    const uint32_t rel = __popc(imask & ~(0xFFFFFFFFu << slot));
+    if (STATS) st.nodes++;
+    // UT_ANY: the item level must see EVERY candidate (the order rule needs them), only BLAS nodes are clipped
+    const float tm = (MODE == UT_ANY && L.blas_base < 0) ? 3.402823466e+38f : L.tmax;
+    node_test(S.nodes, base + rel, L.r, 0.0f, tm, L.ng, L.tg);
+}
+
+// UT_ANY bookkeeping: `bitem/bkey` = the occluder found (an item with a hit at toi <= len), `okey/oitem` (kept in
+// bprim/bface as raw bits) = the earliest (key, index) among all OTHER candidate items.  The any-hit answer is final
+// unless such a candidate sorts before the occluder (then the reference's first-hit rule may stop at it instead).
+__device__ __forceinline__ void lane_note_other(Lane& L, float key, uint32_t item) {
+    const float ok = __uint_as_float(L.bprim);
+    if (L.bface == 0xFFFFFFFFu || key < ok || (key == ok && item < L.bface)) { L.bprim = __float_as_uint(key); L.bface = item; }
+}
+__device__ __forceinline__ void lane_any_hit(Lane& L, float key, uint32_t item) {
+    L.bitem = item; L.bkey = key; L.bflags = 1u;                          // bflags = 1: enumeration mode (no more BLAS work)
+    if (L.blas_base >= 0) { L.sp = L.blas_base; L.blas_base = -1; L.r = L.w; }
+    L.ng = make_uint2(0u, 0u); L.tg = make_uint2(0u, 0u);
+}
+
+template <int MODE, bool STATS>
+__device__ __forceinline__ void lane_leaf(Lane& L, uint2* __restrict__ stack, const SceneDev& S, bool for_shadow, uint32_t depth,
+                                          TravStats& st, uint32_t& n_items, uint32_t& n_sph) {
+    const uint32_t ti = bfind(L.tg.y);
+    L.tg.y &= ~(1u << ti);
+    const uint32_t prim = L.tg.x + ti;
+    if (L.blas_base >= 0) {                                               // triangle of the current item
+        const float4* tp = S.tris + (size_t)prim * 3;
+        const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+        if (STATS) st.tris++;
+        float toi; uint32_t back;
+        if (tri_cast(f3(v0.x, v0.y, v0.z), f3(v1.x, v1.y, v1.z), f3(v2.x, v2.y, v2.z), L.r.o, L.r.d, toi, back)) {
+            if (MODE == UT_CLOSEST) lane_accept(L, toi, L.cur_key, L.cur_item, prim, __float_as_uint(v0.w), back);
+            else if (toi <= L.tmax) lane_any_hit(L, L.cur_key, L.cur_item);
+        }
+        return;
+    }
+    const uint32_t ii = __ldg(S.tlas_prims + prim);                       // item of the TLAS
+    const DItem* it = S.items + ii;
+    const uint32_t flags = it->flags;
+    if (!item_passes(flags, for_shadow, depth)) return;
+    float4 inv[3] = {__ldg(&it->inv[0]), __ldg(&it->inv[1]), __ldg(&it->inv[2])};
+    const float3 lo3 = xform_point(inv, L.w.o), ld3 = xform_vec(inv, L.w.d);
+    const float4 lo = __ldg(&it->lo), hi = __ldg(&it->hi);
+    const bool solid = item_solid(flags, for_shadow);
+    float key;
+    if (STATS) n_items++;
+    if (!aabb_cast(f3(lo.x, lo.y, lo.z), f3(hi.x, hi.y, hi.z), lo3, ld3, solid, key)) return;
+    if (MODE == UT_ANY && L.bflags != 0u) { lane_note_other(L, key, ii); return; }    // occluder known: only enumerate
+    if (!(flags & IF_MESH)) {
+        float t; bool inside;
+        if (STATS) n_sph++;
+        const bool h = ball_cast(lo.w, lo3, ld3, solid, t, inside);
+        if (MODE == UT_CLOSEST) { if (h) lane_accept(L, t, key, ii, 0u, 0u, inside ? HF_INSIDE : 0u); }
+        else if (h && t <= L.tmax) lane_any_hit(L, key, ii);
+        else lane_note_other(L, key, ii);
+        return;
+    }
+    if (MODE == UT_ANY) lane_note_other(L, key, ii);                      // harmless if it becomes the occluder: (key, item) is then not < itself
+    // enter the instance: park what is left of the TLAS groups under the BLAS part of the stack
+    if (L.sp + 2 > kLaneStack) { atomicAdd(S.dbg, 1u); return; }
+    if (L.ng.y > 0x00FFFFFFu) stack[L.sp++] = L.ng;
+    if (L.tg.y != 0u) stack[L.sp++] = L.tg;
+    L.blas_base = L.sp; L.cur_item = ii; L.cur_key = key;
+    L.r = make_wide_ray(lo3, ld3);
+    L.ng = make_uint2(it->root, 0x80000000u); L.tg = make_uint2(0u, 0u);
+}
+
+// Both groups empty: leave the instance if its part of the stack is drained, then pop.  Returns true when the ray is done.
+__device__ __forceinline__ bool lane_pop(Lane& L, const uint2* __restrict__ stack) {
+    if (L.blas_base >= 0 && L.sp == L.blas_base) { L.blas_base = -1; L.r = L.w; }
+    if (L.sp == 0) return true;
+    const uint2 e = stack[--L.sp];
+    if (e.y > 0x00FFFFFFu) L.ng = e; else L.tg = e;
+    return false;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -660,15 +794,21 @@ __device__ __forceinline__ bool get_tex_color(const SceneDev& S, const DMaterial
 // ------------------------------------------------------------------------------------------------
 // shading helpers (reference src/raytracing.rs:492-626)
 // ------------------------------------------------------------------------------------------------
+// Ray geometry is computed with the never-contracted helpers: whether a child ray exists (total internal
+// reflection) and what it hits must not depend on FMA contraction, or ray totals drift from the reference's.
 __device__ __forceinline__ bool create_transmission(float3 normal, float3 incident, float3 p, float index, float3& o, float3& d) {
-    float3 ref_n = normal; float eta_t = index, eta_i = 1.0f; float i_dot_n = dot3(incident, normal);
-    if (i_dot_n < 0.0f) i_dot_n = -i_dot_n; else { ref_n = -normal; eta_t = 1.0f; eta_i = index; }
-    const float eta = eta_i / eta_t;
-    const float k = 1.0f - (eta * eta) * (1.0f - i_dot_n * i_dot_n);
+    float3 ref_n = normal; float eta_t = index, eta_i = 1.0f; float i_dot_n = xdot(incident, normal);
+    if (i_dot_n < 0.0f) i_dot_n = -i_dot_n; else { ref_n = xneg(normal); eta_t = 1.0f; eta_i = index; }
+    const float eta = xd(eta_i, eta_t);
+    const float k = xs(1.0f, xm(xm(eta, eta), xs(1.0f, xm(i_dot_n, i_dot_n))));
     if (k < 0.0f) return false;
-    o = p + ref_n * (-0.001f);
-    d = (incident + i_dot_n * ref_n) * eta - ref_n * sqrtf(k);
+    o = xadd(p, xscale(ref_n, -0.001f));
+    d = xsub(xscale(xadd(incident, xscale(ref_n, i_dot_n)), eta), xscale(ref_n, xsqrt(k)));
     return true;
+}
+__device__ __forceinline__ void create_reflection(float3 normal, float3 incident, float3 p, float3& o, float3& d) {
+    o = xadd(p, xscale(normal, 0.001f));
+    d = xsub(incident, xscale(normal, xm(2.0f, xdot(incident, normal))));
 }
 __device__ __forceinline__ float fresnel(float3 incident, float3 normal, float index) {
     const float i_dot_n = dot3(incident, normal);

@@ -81,24 +81,63 @@ __global__ void __launch_bounds__(256) raygen_kernel(FrameDev F, const uint32_t*
 }
 
 // ---- K2 ------------------------------------------------------------------------------------------
+// Persistent threads with dynamic ray fetch: every lane owns one ray and one traversal state; when fewer than
+// kRefill lanes of a warp still have a ray, the warp leaves the step loop and the idle lanes take new rays
+// (one atomicAdd per warp).  All 32 lanes meet at a ballot after every step, so a step is the unit of divergence.
+#ifndef RTX_REFILL
+#define RTX_REFILL 24
+#endif
+#ifndef RTX_LEAF_BATCH
+#define RTX_LEAF_BATCH 8
+#endif
+constexpr int kRefill = RTX_REFILL;        // refill the warp when fewer lanes than this still own a ray
+constexpr int kLeafBatch = RTX_LEAF_BATCH;  // run a leaf phase when at least this many lanes have pending leaf entries
+constexpr uint32_t kFull = 0xffffffffu;
+
 template <bool STATS>
 __global__ void __launch_bounds__(kTraceBlock) closest_kernel(SceneDev S, RayQ q, uint32_t q_base, uint32_t n, HitRec* __restrict__ hits,
                                                               uint32_t* work, Counters* ctr) {
     TravStats st{0, 0}; uint32_t n_items = 0, n_sph = 0;
+    uint2 stack[kLaneStack];
+    Lane L; bool has = false, exhausted = false; uint32_t my = 0, depth = 1;
     const uint32_t lane = threadIdx.x & 31u;
     for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(work, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        const uint32_t i = base + lane;
-        if (i < n) {
-            const float4 ro = q.o[q_base + i], rd = q.d[q_base + i];
-            const uint32_t depth = (q.m[q_base + i].x >> 16) & 0xffu;
-            Best best;
-            trace_closest<STATS>(S, f3(ro.x, ro.y, ro.z), f3(rd.x, rd.y, rd.z), false, depth, best, st, n_items, n_sph);
-            HitRec h; h.t = best.t; h.item = best.item; h.prim = best.prim; h.flags = best.flags;
-            hits[i] = h;
+        const uint32_t idle = __ballot_sync(kFull, !has);
+        if (idle != 0u && !exhausted) {
+            const uint32_t leader = __ffs(idle) - 1u, cnt = __popc(idle);
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(work, cnt);
+            base = __shfl_sync(kFull, base, leader);
+            if (!has) {
+                const uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
+                if (i < n) {
+                    const float4 ro = q.o[q_base + i], rd = q.d[q_base + i];
+                    depth = (q.m[q_base + i].x >> 16) & 0xffu;
+                    lane_init(L, S, f3(ro.x, ro.y, ro.z), f3(rd.x, rd.y, rd.z), 3.402823466e+38f);
+                    has = true; my = i;
+                }
+            }
+            if (base + cnt >= n) exhausted = true;
+        }
+        if (!__any_sync(kFull, has)) break;
+        for (;;) {
+            // NODE phase for every lane with a pending node group, then a LEAF round when enough lanes have leaf
+            // entries pending (or nobody has node work left)
+            if (has && L.ng.y > 0x00FFFFFFu) lane_node<UT_CLOSEST, STATS>(L, stack, S, st);
+            {
+                const bool want_leaf = has && L.tg.y != 0u;
+                const uint32_t ml = __ballot_sync(kFull, want_leaf);
+                if (ml != 0u && (__popc(ml) >= kLeafBatch || !__any_sync(kFull, has && L.ng.y > 0x00FFFFFFu))) {
+                    if (want_leaf) lane_leaf<UT_CLOSEST, STATS>(L, stack, S, false, depth, st, n_items, n_sph);
+                }
+            }
+            if (has && L.ng.y <= 0x00FFFFFFu && L.tg.y == 0u && lane_pop(L, stack)) {
+                HitRec h; h.t = L.tmax; h.item = L.bitem; h.prim = L.bprim; h.flags = L.bflags;
+                hits[my] = h;
+                has = false;
+            }
+            const uint32_t act = __ballot_sync(kFull, has);
+            if (act == 0u || (!exhausted && __popc(act) < kRefill)) break;
         }
     }
     if (STATS) {
@@ -108,52 +147,119 @@ __global__ void __launch_bounds__(kTraceBlock) closest_kernel(SceneDev S, RayQ q
 }
 
 // ---- K3 ------------------------------------------------------------------------------------------
-template <bool STATS, bool ORDERED>
-__global__ void __launch_bounds__(kTraceBlock) shadow_kernel(SceneDev S, FrameDev F, ShadowQ q, const uint32_t* __restrict__ n_ptr, uint32_t depth,
-                                                             uint32_t* work, Counters* ctr) {
-    TravStats st{0, 0};
+// Shadow rays in two kernels.  K3a answers the order-independent half of the query ("does ANY item that casts
+// shadows have a hit at toi <= light distance") with the same persistent any-hit traversal; a ray with no such
+// hit is lit and done.  An occluded ray is final when the reference's first-hit order cannot change the result
+// (directional light and no alpha-textured material in the scene); the others are compacted into `slow` and
+// K3b re-walks them item by item in the reference's bbox-key order (trace_shadow_fast).
+template <bool STATS>
+__global__ void __launch_bounds__(kTraceBlock) shadow_any_kernel(SceneDev S, FrameDev F, ShadowQ q, const uint32_t* __restrict__ n_ptr, uint32_t depth,
+                                                                 uint32_t* work, uint32_t* __restrict__ slow, uint32_t* slow_count, Counters* ctr) {
+    TravStats st{0, 0}; uint32_t n_items = 0, n_sph = 0;
+    uint2 stack[kLaneStack];
+    Lane L; bool has = false, exhausted = false; uint32_t my = 0;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = *n_ptr;
     for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(work, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        const uint32_t i = base + lane;
-        if (i < n) {
-            const float4 ro = q.o[i], rd = q.d[i], rc = q.c[i];
-            const float3 o = f3(ro.x, ro.y, ro.z), d = f3(rd.x, rd.y, rd.z);
-            const float len = ro.w;
-            const uint32_t pixel = __float_as_uint(rd.w);
-            Best b;
-            bool in_light;
-            if (ORDERED) {
-                trace_shadow_ordered<STATS>(S, o, d, depth, b, st);
-                in_light = b.item == 0xFFFFFFFFu || b.t > len;                  // :885-892 (len = +inf for directional)
-            } else {
-                trace_shadow_fast<STATS>(S, o, d, depth, len, b, st);
-                in_light = b.item == 0xFFFFFFFFu;
-            }
-            float k = 1.0f;
-            if (!in_light) {                                                    // :895-913
-                float ssa = rc.w;
-                const DItem& occ = S.items[b.item];
-                if (occ.flags & IF_ALPHA_TEX) {
-                    const DItem& recv = S.items[q.r[i]];
-                    uint32_t face_id = 0;
-                    if (occ.flags & IF_MESH) {
-                        const uint32_t face = __float_as_uint(__ldg(S.tris + (size_t)b.prim * 3).w);
-                        face_id = (b.flags & HF_BACK) ? face + occ.n_faces : face;
-                    }
-                    const float3 shp = o + d * b.t;
-                    float u, v; item_get_uv(S, recv, shp, face_id, u, v);        // receiver's get_uv (sic, :905)
-                    float4 tc;
-                    if (get_tex_color(S, S.mats[occ.material], true, u, v, 4 /*Alpha*/, tc)) ssa *= tc.x;
+        const uint32_t idle = __ballot_sync(kFull, !has);
+        if (idle != 0u && !exhausted) {
+            const uint32_t leader = __ffs(idle) - 1u, cnt = __popc(idle);
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(work, cnt);
+            base = __shfl_sync(kFull, base, leader);
+            if (!has) {
+                const uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
+                if (i < n) {
+                    const float4 ro = q.o[i], rd = q.d[i];
+                    lane_init(L, S, f3(ro.x, ro.y, ro.z), f3(rd.x, rd.y, rd.z), ro.w);
+                    has = true; my = i;
                 }
-                k = 1.0f - ssa;
             }
-            atomicAdd(&F.accum_c[pixel], make_float4(rc.x * k, rc.y * k, rc.z * k, 0.0f));
+            if (base + cnt >= n) exhausted = true;
         }
+        if (!__any_sync(kFull, has)) break;
+        for (;;) {
+            // NODE phase for every lane with a pending node group, then a LEAF round when enough lanes have leaf
+            // entries pending (or nobody has node work left)
+            if (has && L.ng.y > 0x00FFFFFFu) lane_node<UT_ANY, STATS>(L, stack, S, st);
+            {
+                const bool want_leaf = has && L.tg.y != 0u;
+                const uint32_t ml = __ballot_sync(kFull, want_leaf);
+                if (ml != 0u && (__popc(ml) >= kLeafBatch || !__any_sync(kFull, has && L.ng.y > 0x00FFFFFFu))) {
+                    if (want_leaf) lane_leaf<UT_ANY, STATS>(L, stack, S, true, depth, st, n_items, n_sph);
+                }
+            }
+            bool to_slow = false;
+            if (has && L.ng.y <= 0x00FFFFFFu && L.tg.y == 0u && lane_pop(L, stack)) {
+                has = false;
+                const bool occluded = L.bitem != 0xFFFFFFFFu;
+                const float okey = __uint_as_float(L.bprim);
+                const bool earlier_other = L.bface != 0xFFFFFFFFu && (okey < L.bkey || (okey == L.bkey && L.bface < L.bitem));
+                if (!occluded || (!S.any_alpha_tex && (L.tmax >= 3.402823466e+38f || !earlier_other))) {
+                    const float4 rc = q.c[my];
+                    const float k = occluded ? 1.0f - rc.w : 1.0f;               // raytracing.rs:898,912
+                    atomicAdd(&F.accum_c[__float_as_uint(q.d[my].w)], make_float4(rc.x * k, rc.y * k, rc.z * k, 0.0f));
+                } else to_slow = true;
+            }
+            const uint32_t sm = __ballot_sync(kFull, to_slow);
+            if (sm != 0u) {
+                const uint32_t leader = __ffs(sm) - 1u;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(slow_count, __popc(sm));
+                base = __shfl_sync(kFull, base, leader);
+                if (to_slow) slow[base + __popc(sm & ((1u << lane) - 1u))] = my;
+            }
+            const uint32_t act = __ballot_sync(kFull, has);
+            if (act == 0u || (!exhausted && __popc(act) < kRefill)) break;
+        }
+    }
+    if (STATS) {
+        atomicAdd(&ctr->node_visits[1], (unsigned long long)st.nodes); atomicAdd(&ctr->tri_tests[1], (unsigned long long)st.tris);
+        atomicAdd(&ctr->item_tests, (unsigned long long)n_items); atomicAdd(&ctr->sphere_tests, (unsigned long long)n_sph);
+    }
+}
+
+// K3b: reference-order walk.  `slow` == nullptr: all rays of the queue (RTX_DEBUG_ORDERED_SHADOW runs the literal
+// "closest hit of every item in order" version on everything, without K3a).
+template <bool STATS, bool ORDERED>
+__global__ void __launch_bounds__(kTraceBlock) shadow_exact_kernel(SceneDev S, FrameDev F, ShadowQ q, const uint32_t* __restrict__ slow,
+                                                                   const uint32_t* __restrict__ n_ptr, uint32_t depth, Counters* ctr) {
+    TravStats st{0, 0};
+    const uint32_t n = *n_ptr;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const uint32_t i = slow ? slow[j] : j;
+        const float4 ro = q.o[i], rd = q.d[i], rc = q.c[i];
+        const float3 o = f3(ro.x, ro.y, ro.z), d = f3(rd.x, rd.y, rd.z);
+        const float len = ro.w;
+        const uint32_t pixel = __float_as_uint(rd.w);
+        Best b;
+        bool in_light;
+        if (ORDERED) {
+            trace_shadow_ordered<STATS>(S, o, d, depth, b, st);
+            in_light = b.item == 0xFFFFFFFFu || b.t > len;                  // :885-892 (len = +inf for directional)
+        } else {
+            trace_shadow_fast<STATS>(S, o, d, depth, len, b, st);
+            in_light = b.item == 0xFFFFFFFFu;
+        }
+        float k = 1.0f;
+        if (!in_light) {                                                    // :895-913
+            float ssa = rc.w;
+            const DItem& occ = S.items[b.item];
+            if (occ.flags & IF_ALPHA_TEX) {
+                const DItem& recv = S.items[q.r[i]];
+                uint32_t face_id = 0;
+                if (occ.flags & IF_MESH) {
+                    const uint32_t face = __float_as_uint(__ldg(S.tris + (size_t)b.prim * 3).w);
+                    face_id = (b.flags & HF_BACK) ? face + occ.n_faces : face;
+                }
+                const float3 shp = o + d * b.t;
+                float u, v; item_get_uv(S, recv, shp, face_id, u, v);        // receiver's get_uv (sic, :905)
+                float4 tc;
+                if (get_tex_color(S, S.mats[occ.material], true, u, v, 4 /*Alpha*/, tc)) ssa *= tc.x;
+            }
+            k = 1.0f - ssa;
+        }
+        atomicAdd(&F.accum_c[pixel], make_float4(rc.x * k, rc.y * k, rc.z * k, 0.0f));
     }
     if (STATS) { atomicAdd(&ctr->node_visits[1], (unsigned long long)st.nodes); atomicAdd(&ctr->tri_tests[1], (unsigned long long)st.tris); }
 }
@@ -203,22 +309,22 @@ __global__ void __launch_bounds__(kShadeBlock) shade_kernel(SceneDev S, FrameDev
             }
             if (rflags & RF_ID_OWNER) F.ids[pixel] = item.id;
             surface_normal = normal;
-            hit_point = o + (d * hit_dist);
+            hit_point = xadd(o, xscale(d, hit_dist));
             const bool has_uv = mat.any_texture != 0;
             float u = 0.0f, v = 0.0f;
             if (has_uv) item_get_uv(S, item, hit_point, face_id, u, v);
             float4 tc;
             if (get_tex_color(S, mat, has_uv, u, v, 3 /*Normal*/, tc)) {          // :757-784
-                float3 tangent = cross3(normal, f3(0, 1, 0));
-                if (len3(tangent) <= 0.0001f) tangent = cross3(normal, f3(0, 0, 1));
-                tangent = norm3(tangent);
-                const float3 bitangent = norm3(cross3(normal, tangent));
-                float3 nm = f3(tc.x * 2.0f - 1.0f, tc.y * 2.0f - 1.0f, tc.z * 2.0f - 1.0f);
-                nm.x *= mat.normal_map_strength; nm.y *= mat.normal_map_strength;
-                nm = norm3(nm);
-                surface_normal = norm3(f3((tangent.x * nm.x + bitangent.x * nm.y) + normal.x * nm.z,
-                                          (tangent.y * nm.x + bitangent.y * nm.y) + normal.y * nm.z,
-                                          (tangent.z * nm.x + bitangent.z * nm.y) + normal.z * nm.z));
+                float3 tangent = xcross(normal, f3(0, 1, 0));
+                if (xnorm(tangent) <= 0.0001f) tangent = xcross(normal, f3(0, 0, 1));
+                tangent = xnormalize(tangent);
+                const float3 bitangent = xnormalize(xcross(normal, tangent));
+                float3 nm = f3(xs(xm(tc.x, 2.0f), 1.0f), xs(xm(tc.y, 2.0f), 1.0f), xs(xm(tc.z, 2.0f), 1.0f));
+                nm.x = xm(nm.x, mat.normal_map_strength); nm.y = xm(nm.y, mat.normal_map_strength);
+                nm = xnormalize(nm);
+                surface_normal = xnormalize(f3(xa(xa(xm(tangent.x, nm.x), xm(bitangent.x, nm.y)), xm(normal.x, nm.z)),
+                                               xa(xa(xm(tangent.y, nm.x), xm(bitangent.y, nm.y)), xm(normal.y, nm.z)),
+                                               xa(xa(xm(tangent.z, nm.x), xm(bitangent.z, nm.y)), xm(normal.z, nm.z))));
             }
             const bool has_rough = get_tex_color(S, mat, has_uv, u, v, 5 /*Roughness*/, tc);   // :787-798
             if (F.monte_carlo && mat.monte_carlo && (mat.roughness > 0.0f || has_rough)) {
@@ -254,8 +360,7 @@ __global__ void __launch_bounds__(kShadeBlock) shade_kernel(SceneDev S, FrameDev
                           wgt * (ao * fog * F.fog_color[2] + ambient_color.z));
             if (reflect_on) {                                                     // :492-498
                 emit_refl = true; w_refl = thru * a * reflectivity;
-                refl_o = hit_point + surface_normal * 0.001f;
-                refl_d = d - (2.0f * dot3(d, surface_normal)) * surface_normal;
+                create_reflection(surface_normal, d, hit_point, refl_o, refl_d);
             }
             if (trans_exists) {
                 emit_trans = true; w_trans = thru * kt;
@@ -272,7 +377,7 @@ __global__ void __launch_bounds__(kShadeBlock) shade_kernel(SceneDev S, FrameDev
             bool emit = false; float3 sdir = f3(0, 0, 1), c = f3(0, 0, 0); float len = 3.402823466e+38f;
             if (hit) {
                 const float3 lpos = f3(L.pos[0], L.pos[1], L.pos[2]), ldir = f3(L.dir[0], L.dir[1], L.dir[2]);
-                const float3 dtl = L.type == 0 ? norm3(-ldir) : norm3(lpos - hit_point);
+                const float3 dtl = L.type == 0 ? xnormalize(xneg(ldir)) : xnormalize(xsub(lpos, hit_point));
                 const float dot_light = fmaxf(dot3(surface_normal, dtl), 0.0f);
                 const float3 mi = -dtl;
                 const float3 reflect_dir = mi - (2.0f * dot3(surface_normal, mi)) * surface_normal;
@@ -282,7 +387,7 @@ __global__ void __launch_bounds__(kShadeBlock) shade_kernel(SceneDev S, FrameDev
                 float intensity;
                 if (L.type == 0) intensity = L.intensity;
                 else {
-                    const float r2 = len3(lpos - hit_point);
+                    const float r2 = xnorm(xsub(lpos, hit_point));
                     intensity = L.intensity / (4.0f * PI * r2);
                     len = r2;
                     if (L.type == 2) {
@@ -303,7 +408,7 @@ __global__ void __launch_bounds__(kShadeBlock) shade_kernel(SceneDev S, FrameDev
             const uint32_t slot = queue_append(out.shadow_count, emit);
             if (emit) {
                 if (slot < out.shadow_cap) {
-                    const float3 so = hit_point + surface_normal * 0.001f;
+                    const float3 so = xadd(hit_point, xscale(surface_normal, 0.001f));
                     out.shadow.o[slot] = make_float4(so.x, so.y, so.z, len);
                     out.shadow.d[slot] = make_float4(sdir.x, sdir.y, sdir.z, __uint_as_float(pixel));
                     out.shadow.c[slot] = make_float4(c.x, c.y, c.z, mat_alpha);
@@ -397,6 +502,50 @@ __global__ void probe_kernel(SceneDev S, const ProbeRay* __restrict__ rays, uint
         h.t = b.t; h.n[0] = nn.x; h.n[1] = nn.y; h.n[2] = nn.z; h.item_id = it.id; h.face_id = face_id; h.item_index = (int32_t)b.item;
     }
     out[i] = h;
+}
+
+// probe through the PRODUCTION closest-hit kernel: pack probe rays into a ray queue, run closest_kernel, convert
+__global__ void probe_pack_kernel(const ProbeRay* __restrict__ rays, uint32_t n, uint32_t depth, RayQ q) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    q.o[i] = make_float4(rays[i].o[0], rays[i].o[1], rays[i].o[2], 1.0f);
+    q.d[i] = make_float4(rays[i].d[0], rays[i].d[1], rays[i].d[2], 0.0f);
+    q.m[i] = make_uint2((depth & 0xffu) << 16, 1u);
+}
+__global__ void probe_unpack_kernel(SceneDev S, const ProbeRay* __restrict__ rays, const HitRec* __restrict__ hits, uint32_t n, ProbeHit* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const HitRec b = hits[i];
+    ProbeHit h; h.reserved = 0;
+    if (b.item == 0xFFFFFFFFu) { h.t = -1.0f; h.n[0] = h.n[1] = h.n[2] = 0.0f; h.item_id = 0; h.face_id = 0; h.item_index = -1; }
+    else {
+        const DItem& it = S.items[b.item];
+        uint32_t face_id;
+        const float3 nn = hit_normal(S, it, f3(rays[i].o[0], rays[i].o[1], rays[i].o[2]), f3(rays[i].d[0], rays[i].d[1], rays[i].d[2]), b.t, b.prim, b.flags, face_id);
+        h.t = b.t; h.n[0] = nn.x; h.n[1] = nn.y; h.n[2] = nn.z; h.item_id = it.id; h.face_id = face_id; h.item_index = (int32_t)b.item;
+    }
+    out[i] = h;
+}
+
+// debug (RTX_VERIFY=1): recompute every closest hit of a wave with the simple per-thread traversal and record mismatches
+struct VerifyRec { float o[3], d[3]; uint32_t depth, index; float t_prod; uint32_t item_prod, prim_prod; float t_ref; uint32_t item_ref, prim_ref; };
+__global__ void verify_closest_kernel(SceneDev S, RayQ q, uint32_t q_base, uint32_t n, const HitRec* __restrict__ hits, uint32_t* count, VerifyRec* recs, uint32_t cap) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 ro = q.o[q_base + i], rd = q.d[q_base + i];
+    const uint32_t depth = (q.m[q_base + i].x >> 16) & 0xffu;
+    Best b; TravStats st{0, 0}; uint32_t a = 0, c = 0;
+    trace_closest<false>(S, f3(ro.x, ro.y, ro.z), f3(rd.x, rd.y, rd.z), false, depth, b, st, a, c);
+    const HitRec h = hits[i];
+    const bool same = (h.item == b.item) && (b.item == 0xFFFFFFFFu || (h.t == b.t && h.prim == b.prim));
+    if (!same) {
+        const uint32_t k = atomicAdd(count, 1u);
+        if (k < cap) {
+            VerifyRec r; r.o[0] = ro.x; r.o[1] = ro.y; r.o[2] = ro.z; r.d[0] = rd.x; r.d[1] = rd.y; r.d[2] = rd.z; r.depth = depth; r.index = i;
+            r.t_prod = h.t; r.item_prod = h.item; r.prim_prod = h.prim; r.t_ref = b.t; r.item_ref = b.item; r.prim_ref = b.prim;
+            recs[k] = r;
+        }
+    }
 }
 
 // ---- shard pack / unpack ---------------------------------------------------------------------------

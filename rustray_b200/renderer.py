@@ -28,7 +28,8 @@ class RtxError(RuntimeError):
 
 
 def lib_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+    """rustray_b200/librtx_b200.so; RTX_LIB overrides it (tuning variants built by tools/build_variants.sh)."""
+    return os.environ.get("RTX_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
 
 
 def load_library() -> C.CDLL:
