@@ -1,6 +1,10 @@
 // bvh_build.cpp — see bvh_build.h.  Host code, runs once per scene (cold path).
 #include "bvh_build.h"
 
+#ifndef RTX_DEQUANT
+#define RTX_DEQUANT 0     // must match csrc/rtx_device.cuh (0: I2F dequantisation, exact grid)
+#endif
+
 #include <algorithm>
 #include <cassert>
 #include <cmath>
@@ -148,16 +152,33 @@ struct WideBuilder {
 
         WideNode w; memset(&w, 0, sizeof(w));
         for (int k = 0; k < 3; k++) {
+#if RTX_DEQUANT != 0
+            // Quantisation grid with a one-step margin on both sides: child planes land in [1, 254] and are then
+            // padded outward by one step to [0, 255].  The PRMT dequantisation (byte -> 2^23 + q, 2^23 folded into the
+            // FMA addend) costs up to half a step of accuracy; the padding absorbs it.
+            float ext = box.hi[k] - box.lo[k];
+            int eb = 1;
+            if (ext > 0.f) {
+                int ex; std::frexp(ext / 253.0f, &ex);         // ext/253 = m * 2^ex, m in [0.5,1)  =>  2^ex * 253 >= ext
+                eb = std::max(1, std::min(254, ex + 127));
+            }
+            for (;;) {
+                const float scale = std::ldexp(1.0f, eb - 127);
+                w.p[k] = box.lo[k] - scale;
+                if (eb >= 254 || (w.p[k] + scale <= box.lo[k] && w.p[k] + 254.0f * scale >= box.hi[k])) break;
+                eb++;
+            }
+#else
             w.p[k] = box.lo[k];
             float ext = box.hi[k] - box.lo[k];
             int eb = 1;
             if (ext > 0.f) {
                 int ex; std::frexp(ext / 255.0f, &ex);         // ext/255 = m * 2^ex, m in [0.5,1)  =>  2^ex * 255 >= ext
                 eb = ex + 127;
-                // make sure 255 * 2^e really covers the extent in float arithmetic
-                while (eb < 254 && w.p[k] + 255.0f * std::ldexp(1.0f, eb - 127) < box.hi[k]) eb++;
+                while (eb < 254 && w.p[k] + 255.0f * std::ldexp(1.0f, eb - 127) < box.hi[k]) eb++;   // cover the extent in float arithmetic
                 eb = std::max(1, std::min(254, eb));
             }
+#endif
             w.e[k] = (uint8_t)eb;
         }
         uint32_t n_internal = 0;
@@ -177,9 +198,16 @@ struct WideBuilder {
                 float scale = std::ldexp(1.0f, (int)w.e[k] - 127);
                 int lo = (int)std::floor((cn.box.lo[k] - w.p[k]) / scale);
                 int hi = (int)std::ceil((cn.box.hi[k] - w.p[k]) / scale);
+#if RTX_DEQUANT != 0
+                lo = std::max(1, std::min(254, lo)); hi = std::max(1, std::min(254, hi));
+                while (lo > 1 && w.p[k] + (float)lo * scale > cn.box.lo[k]) lo--;
+                while (hi < 254 && w.p[k] + (float)hi * scale < cn.box.hi[k]) hi++;
+                lo -= 1; hi += 1;                                  // the half-step slack of the PRMT conversion
+#else
                 lo = std::max(0, std::min(255, lo)); hi = std::max(0, std::min(255, hi));
                 while (lo > 0 && w.p[k] + (float)lo * scale > cn.box.lo[k]) lo--;
                 while (hi < 255 && w.p[k] + (float)hi * scale < cn.box.hi[k]) hi++;
+#endif
                 w.qlo[k][s] = (uint8_t)lo; w.qhi[k][s] = (uint8_t)hi;
             }
             if (cn.count == 0) {

@@ -123,6 +123,11 @@ void fill_item(const RtxScene& sc, const RtxItem& s, DItem& d) {
     if (c_alpha > 0.0f) f |= IF_ALPHA_POS;
     if (c_alpha < 1.0f) f |= IF_ALPHA_LT1;
     if (m.texture[RTX_TEX_ALPHA] >= 0) f |= IF_ALPHA_TEX;
+    {   // identity + translation inverse (planes, spheres): the per-item ray transform degenerates to one add per axis
+        const float* t = s.tran_inverse;
+        if (t[0] == 1.f && t[5] == 1.f && t[10] == 1.f && t[1] == 0.f && t[2] == 0.f && t[4] == 0.f && t[6] == 0.f && t[8] == 0.f && t[9] == 0.f)
+            f |= IF_TRANSLATION;
+    }
     d.id = s.id; d.material = (uint32_t)s.material;
     d.lo.w = s.radius; d.hi.w = c_alpha;
     d.flags = f;
@@ -185,6 +190,7 @@ void refresh_dev(RtxScene& sc) {
     if (!sc.overflow.p) sc.overflow.alloc(4);
     D.dbg = sc.overflow.p + 1;
     D.any_alpha_tex = 0u;
+    D.flat_items = (!sc.h_items.empty() && sc.h_items.size() <= 24 && getenv("RTX_FLAT_ITEMS")) ? ((1u << sc.h_items.size()) - 1u) : 0u;   // measured slower than the 1-node TLAS (it prunes item visits)
     for (const DItem& it : sc.h_items) if (it.flags & IF_ALPHA_TEX) D.any_alpha_tex = 1u;
 }
 
@@ -490,6 +496,9 @@ int rtx_scene_update_items(RtxScene* sc, const RtxItemXform* x, size_t n) {
             d.inv[r] = make_float4(s.tran_inverse[0 + r], s.tran_inverse[4 + r], s.tran_inverse[8 + r], s.tran_inverse[12 + r]);
             d.mat[r] = make_float4(s.trans[0 + r], s.trans[4 + r], s.trans[8 + r], s.trans[12 + r]);
         }
+        const float* t = s.tran_inverse;
+        const bool tr = t[0] == 1.f && t[5] == 1.f && t[10] == 1.f && t[1] == 0.f && t[2] == 0.f && t[4] == 0.f && t[6] == 0.f && t[8] == 0.f && t[9] == 0.f;
+        d.flags = tr ? (d.flags | IF_TRANSLATION) : (d.flags & ~IF_TRANSLATION);
     }
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(sc->items.p, sc->h_items.data(), sc->h_items.size() * sizeof(DItem), cudaMemcpyHostToDevice));

@@ -21,7 +21,8 @@ namespace rtx {
 // ------------------------------------------------------------------------------------------------
 enum : uint32_t {
     IF_MESH = 1u, IF_VISIBLE = 2u, IF_FLIP = 4u, IF_CAST_SHADOW = 8u, IF_REFL_ONLY = 16u, IF_BACKFACE = 32u,
-    IF_SMOOTH = 64u, IF_HAS_NORMALS = 128u, IF_ALPHA_TEX = 256u, IF_ALPHA_POS = 512u, IF_ALPHA_LT1 = 1024u
+    IF_SMOOTH = 64u, IF_HAS_NORMALS = 128u, IF_ALPHA_TEX = 256u, IF_ALPHA_POS = 512u, IF_ALPHA_LT1 = 1024u,
+    IF_TRANSLATION = 2048u     // tran_inverse is identity + translation: o' = o + t, d' = d (bit-identical to the general product)
 };
 
 struct alignas(16) DItem {
@@ -53,7 +54,7 @@ struct SceneDev {
     const float* verts; const uint32_t* idx; const float* uvs; const uint32_t* uv_idx; const float* nrms; const uint32_t* n_idx;
     const DMaterial* mats; const DTex* texs; const uchar4* texels; const DLight* lights;
     uint32_t n_items, n_lights, tlas_root, use_tlas;
-    uint32_t ball_flip_inside, any_alpha_tex, pad[2];
+    uint32_t ball_flip_inside, any_alpha_tex, flat_items /* bit mask of tlas_prims entries when n_items <= 24, else 0 */, pad;
     uint32_t* dbg;      // debug counters: [0] lane stack overflow
 };
 
@@ -144,7 +145,7 @@ __device__ __forceinline__ bool aabb_cast(float3 lo, float3 hi, float3 o, float3
         if (dd[i] == 0.0f) {
             if (oo[i] < mn[i] || oo[i] > mx[i]) return false;
         } else {
-            float denom = xd(1.0f, dd[i]);
+            float denom = __frcp_rn(dd[i]);                              // == 1.0f / d, correctly rounded
             float n = xm(xs(mn[i], oo[i]), denom), f = xm(xs(mx[i], oo[i]), denom);
             if (n > f) { float t = n; n = f; f = t; }
             tmin = fmaxf(tmin, n);
@@ -203,6 +204,10 @@ __device__ __forceinline__ bool tri_cast(float3 a, float3 b, float3 c, float3 o,
 __device__ __forceinline__ uint32_t sign_extend_s8x4(uint32_t x) { uint32_t r; asm("prmt.b32 %0, %1, 0x0, 0x0000BA98;" : "=r"(r) : "r"(x)); return r; }
 __device__ __forceinline__ uint32_t byte_of(uint32_t x, int j) { return (x >> (8 * j)) & 0xffu; }
 __device__ __forceinline__ uint32_t bfind(uint32_t x) { return 31u - __clz(x); }
+#ifndef RTX_DEQUANT
+#define RTX_DEQUANT 0
+#endif
+__device__ __forceinline__ float byte_as_f23(uint32_t x, int j) { return __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7650u + j)); }   // 2^23 + byte j
 
 struct TravStats { uint32_t nodes, tris; };
 struct MeshHit { float t; uint32_t prim, face, back; };
@@ -242,7 +247,11 @@ __device__ __forceinline__ uint32_t node_test(const float4* __restrict__ nodes, 
     const float px = fmaf(fabsf(ax), 255.0f, fabsf(bx)) * 2e-6f;
     const float py = fmaf(fabsf(ay), 255.0f, fabsf(by)) * 2e-6f;
     const float pz = fmaf(fabsf(az), 255.0f, fabsf(bz)) * 2e-6f;
-    const float blx = bx - px, bhx = bx + px, bly = by - py, bhy = by + py, blz = bz - pz, bhz = bz + pz;
+    // byte q -> float (2^23 + q) with one PRMT; the 2^23 is folded into the addend: q*a + b = (2^23+q)*a + (b - 2^23*a)
+    const float k23 = 8388608.0f;
+    const float blx = fmaf(-k23, ax, bx - px), bhx = fmaf(-k23, ax, bx + px);
+    const float bly = fmaf(-k23, ay, by - py), bhy = fmaf(-k23, ay, by + py);
+    const float blz = fmaf(-k23, az, bz - pz), bhz = fmaf(-k23, az, bz + pz);
     uint32_t hitmask = 0;
 #pragma unroll
     for (int half = 0; half < 2; half++) {
@@ -259,9 +268,19 @@ __device__ __forceinline__ uint32_t node_test(const float4* __restrict__ nodes, 
         const uint32_t zn = r.d.z < 0.0f ? qhiz : qloz, zf = r.d.z < 0.0f ? qloz : qhiz;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const float t0x = fmaf((float)byte_of(xn, j), ax, blx), t1x = fmaf((float)byte_of(xf, j), ax, bhx);
-            const float t0y = fmaf((float)byte_of(yn, j), ay, bly), t1y = fmaf((float)byte_of(yf, j), ay, bhy);
-            const float t0z = fmaf((float)byte_of(zn, j), az, blz), t1z = fmaf((float)byte_of(zf, j), az, bhz);
+#if RTX_DEQUANT == 0      // all six planes through I2F.U8 (XU pipe)
+            const float t0x = fmaf((float)byte_of(xn, j), ax, bx - px), t1x = fmaf((float)byte_of(xf, j), ax, bx + px);
+            const float t0y = fmaf((float)byte_of(yn, j), ay, by - py), t1y = fmaf((float)byte_of(yf, j), ay, by + py);
+            const float t0z = fmaf((float)byte_of(zn, j), az, bz - pz), t1z = fmaf((float)byte_of(zf, j), az, bz + pz);
+#elif RTX_DEQUANT == 1    // all six through PRMT (ALU pipe)
+            const float t0x = fmaf(byte_as_f23(xn, j), ax, blx), t1x = fmaf(byte_as_f23(xf, j), ax, bhx);
+            const float t0y = fmaf(byte_as_f23(yn, j), ay, bly), t1y = fmaf(byte_as_f23(yf, j), ay, bhy);
+            const float t0z = fmaf(byte_as_f23(zn, j), az, blz), t1z = fmaf(byte_as_f23(zf, j), az, bhz);
+#else                     // near planes I2F (XU), far planes PRMT (ALU): balances the two pipes
+            const float t0x = fmaf((float)byte_of(xn, j), ax, bx - px), t1x = fmaf(byte_as_f23(xf, j), ax, bhx);
+            const float t0y = fmaf((float)byte_of(yn, j), ay, by - py), t1y = fmaf(byte_as_f23(yf, j), ay, bhy);
+            const float t0z = fmaf((float)byte_of(zn, j), az, bz - pz), t1z = fmaf(byte_as_f23(zf, j), az, bhz);
+#endif
             const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
             const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
             if (cmin <= cmax) hitmask |= byte_of(child_bits4, j) << byte_of(bit_index4, j);
@@ -578,7 +597,9 @@ struct Lane {
 
 __device__ __forceinline__ void lane_init(Lane& L, const SceneDev& S, float3 o, float3 d, float tmax) {
     L.w = make_wide_ray(o, d); L.r = L.w; L.tmax = tmax;
-    L.ng = make_uint2(S.tlas_root, 0x80000000u); L.tg = make_uint2(0u, 0u); L.sp = 0; L.blas_base = -1;
+    if (S.flat_items) { L.ng = make_uint2(0u, 0u); L.tg = make_uint2(0u, S.flat_items); }      // few items: every item is a leaf entry, no TLAS node
+    else { L.ng = make_uint2(S.tlas_root, 0x80000000u); L.tg = make_uint2(0u, 0u); }
+    L.sp = 0; L.blas_base = -1;
     L.cur_item = 0; L.cur_key = 0.0f; L.bkey = 0.0f; L.bitem = 0xFFFFFFFFu; L.bprim = 0; L.bface = 0xFFFFFFFFu; L.bflags = 0;
 }
 
@@ -647,8 +668,14 @@ __device__ __forceinline__ void lane_leaf(Lane& L, uint2* __restrict__ stack, co
     const DItem* it = S.items + ii;
     const uint32_t flags = it->flags;
     if (!item_passes(flags, for_shadow, depth)) return;
-    float4 inv[3] = {__ldg(&it->inv[0]), __ldg(&it->inv[1]), __ldg(&it->inv[2])};
-    const float3 lo3 = xform_point(inv, L.w.o), ld3 = xform_vec(inv, L.w.d);
+    float3 lo3, ld3;
+    if (flags & IF_TRANSLATION) {                                         // ((1*x + 0*y) + 0*z) + t*1 == x + t for finite inputs
+        const float4 r0 = __ldg(&it->inv[0]), r1 = __ldg(&it->inv[1]), r2 = __ldg(&it->inv[2]);
+        lo3 = f3(xa(L.w.o.x, r0.w), xa(L.w.o.y, r1.w), xa(L.w.o.z, r2.w)); ld3 = L.w.d;
+    } else {
+        float4 inv[3] = {__ldg(&it->inv[0]), __ldg(&it->inv[1]), __ldg(&it->inv[2])};
+        lo3 = xform_point(inv, L.w.o); ld3 = xform_vec(inv, L.w.d);
+    }
     const float4 lo = __ldg(&it->lo), hi = __ldg(&it->hi);
     const bool solid = item_solid(flags, for_shadow);
     float key;

@@ -87,6 +87,9 @@ __global__ void __launch_bounds__(256) raygen_kernel(FrameDev F, const uint32_t*
 #ifndef RTX_REFILL
 #define RTX_REFILL 24
 #endif
+#ifndef RTX_MIN_BLOCKS
+#define RTX_MIN_BLOCKS 7
+#endif
 #ifndef RTX_LEAF_BATCH
 #define RTX_LEAF_BATCH 8
 #endif
@@ -95,7 +98,7 @@ constexpr int kLeafBatch = RTX_LEAF_BATCH;  // run a leaf phase when at least th
 constexpr uint32_t kFull = 0xffffffffu;
 
 template <bool STATS>
-__global__ void __launch_bounds__(kTraceBlock) closest_kernel(SceneDev S, RayQ q, uint32_t q_base, uint32_t n, HitRec* __restrict__ hits,
+__global__ void __launch_bounds__(kTraceBlock, RTX_MIN_BLOCKS) closest_kernel(SceneDev S, RayQ q, uint32_t q_base, uint32_t n, HitRec* __restrict__ hits,
                                                               uint32_t* work, Counters* ctr) {
     TravStats st{0, 0}; uint32_t n_items = 0, n_sph = 0;
     uint2 stack[kLaneStack];
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(kTraceBlock) closest_kernel(SceneDev S, RayQ q
 // (directional light and no alpha-textured material in the scene); the others are compacted into `slow` and
 // K3b re-walks them item by item in the reference's bbox-key order (trace_shadow_fast).
 template <bool STATS>
-__global__ void __launch_bounds__(kTraceBlock) shadow_any_kernel(SceneDev S, FrameDev F, ShadowQ q, const uint32_t* __restrict__ n_ptr, uint32_t depth,
+__global__ void __launch_bounds__(kTraceBlock, RTX_MIN_BLOCKS) shadow_any_kernel(SceneDev S, FrameDev F, ShadowQ q, const uint32_t* __restrict__ n_ptr, uint32_t depth,
                                                                  uint32_t* work, uint32_t* __restrict__ slow, uint32_t* slow_count, Counters* ctr) {
     TravStats st{0, 0}; uint32_t n_items = 0, n_sph = 0;
     uint2 stack[kLaneStack];
@@ -271,7 +274,10 @@ struct ShadeOut {
     uint32_t* overflow;                                         // set to 1 if a queue would overflow (never, by construction)
 };
 
-__global__ void __launch_bounds__(kShadeBlock) shade_kernel(SceneDev S, FrameDev F, RayQ q, uint32_t q_base, uint32_t n, const HitRec* __restrict__ hits,
+#ifndef RTX_SHADE_MIN_BLOCKS
+#define RTX_SHADE_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(kShadeBlock, RTX_SHADE_MIN_BLOCKS) shade_kernel(SceneDev S, FrameDev F, RayQ q, uint32_t q_base, uint32_t n, const HitRec* __restrict__ hits,
                                                             ShadeOut out) {
     const float PI = 3.14159265358979323846f;
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
