@@ -267,9 +267,9 @@ int ensure_frame(RtxScene& sc, uint32_t w, uint32_t h) {
 int ensure_queues(RtxScene& sc, uint32_t max_recursion, uint32_t n_lights_enabled) {
     uint32_t levels = max_recursion + 1;
     if (levels > 64) return fail(RTX_E_INVALID, "max_recursion > 63 is not supported by the wavefront queues");
-    uint32_t chunk = 1u << 21;
+    uint32_t chunk = 1u << 23;                    // rays per wave: bigger waves = fewer kernel tails and host round trips
     if (const char* e = getenv("RTX_CHUNK")) { long v = atol(e); if (v >= 1024) chunk = (uint32_t)v; }
-    while (levels > 12 && chunk > (1u << 17) && (size_t)levels * 3 * chunk * 40 > (size_t)8 << 30) chunk >>= 1;
+    while (chunk > (1u << 17) && (size_t)levels * 3 * chunk * 40 > (size_t)12 << 30) chunk >>= 1;   // <= 12 GB of ray queues
     uint32_t shadow_cap = chunk * std::max(1u, n_lights_enabled);
     if (sc.chunk == chunk && sc.levels >= levels && sc.shadow_cap >= shadow_cap) return RTX_OK;
     sc.chunk = chunk; sc.levels = std::max(sc.levels, levels); sc.level_cap = 3 * chunk; sc.shadow_cap = std::max(sc.shadow_cap, shadow_cap);

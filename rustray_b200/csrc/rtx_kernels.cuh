@@ -93,6 +93,10 @@ __global__ void __launch_bounds__(256) raygen_kernel(FrameDev F, const uint32_t*
 #ifndef RTX_LEAF_BATCH
 #define RTX_LEAF_BATCH 8
 #endif
+#ifndef RTX_NODE_REPS
+#define RTX_NODE_REPS 1
+#endif
+constexpr int kNodeReps = RTX_NODE_REPS;   // node phases per loop iteration
 constexpr int kRefill = RTX_REFILL;        // refill the warp when fewer lanes than this still own a ray
 constexpr int kLeafBatch = RTX_LEAF_BATCH;  // run a leaf phase when at least this many lanes have pending leaf entries
 constexpr uint32_t kFull = 0xffffffffu;
@@ -126,6 +130,11 @@ __global__ void __launch_bounds__(kTraceBlock, RTX_MIN_BLOCKS) closest_kernel(Sc
         for (;;) {
             // NODE phase for every lane with a pending node group, then a LEAF round when enough lanes have leaf
             // entries pending (or nobody has node work left)
+#pragma unroll
+            for (int rep = 0; rep < kNodeReps - 1; rep++) {                    // extra node phases per iteration amortise the votes below
+                if (has && L.ng.y > 0x00FFFFFFu) lane_node<UT_CLOSEST, STATS>(L, stack, S, st);
+                if (has && L.ng.y <= 0x00FFFFFFu && L.tg.y == 0u && L.sp != 0 && !(L.blas_base >= 0 && L.sp == L.blas_base)) lane_pop(L, stack);
+            }
             if (has && L.ng.y > 0x00FFFFFFu) lane_node<UT_CLOSEST, STATS>(L, stack, S, st);
             {
                 const bool want_leaf = has && L.tg.y != 0u;
@@ -184,6 +193,11 @@ __global__ void __launch_bounds__(kTraceBlock, RTX_MIN_BLOCKS) shadow_any_kernel
         for (;;) {
             // NODE phase for every lane with a pending node group, then a LEAF round when enough lanes have leaf
             // entries pending (or nobody has node work left)
+#pragma unroll
+            for (int rep = 0; rep < kNodeReps - 1; rep++) {                    // extra node phases per iteration amortise the votes below
+                if (has && L.ng.y > 0x00FFFFFFu) lane_node<UT_ANY, STATS>(L, stack, S, st);
+                if (has && L.ng.y <= 0x00FFFFFFu && L.tg.y == 0u && L.sp != 0 && !(L.blas_base >= 0 && L.sp == L.blas_base)) lane_pop(L, stack);
+            }
             if (has && L.ng.y > 0x00FFFFFFu) lane_node<UT_ANY, STATS>(L, stack, S, st);
             {
                 const bool want_leaf = has && L.tg.y != 0u;
