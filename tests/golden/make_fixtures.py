@@ -24,6 +24,8 @@ SCENES = {
     "c2_floor_monkey": (["scene/floor.json", "scene/monkey.json"], 1280, 720, 32, True),
     "room_spheres": (["scene/room-no-textures.json", "scene/spheres.json"], 1280, 720, 128, True),
     "kbert": (["scene/floor.json", "scene/kbert.json"], 1280, 720, 64, True),
+    # glTF path (easy-gltf semantics: de-indexed mesh, file camera + KHR lights, PBR material with roughness jitter)
+    "monkey_gltf": (["scene/models/monkey/monkey.gltf"], 1280, 720, 16, True),
 }
 
 

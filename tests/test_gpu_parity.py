@@ -22,7 +22,7 @@ from tests.util import clone_cfg, lsb_stats, psnr, random_rays, scene_to_abi
 
 pytestmark = pytest.mark.gpu
 
-FIXTURES = ["c1_spheres", "c2_floor_monkey", "room_spheres", "kbert"]
+FIXTURES = ["c1_spheres", "c2_floor_monkey", "room_spheres", "kbert", "monkey_gltf"]
 
 
 def _pair(fs, w, h):
@@ -213,6 +213,30 @@ def test_update_items_and_lights_between_frames():
         fg, fc = g.start(cam, cfg), c.render(cam, cfg)
         assert lsb_stats(fg.image, fc.image)[0] >= 0.999 and np.array_equal(fg.objects, fc.objects)
         assert (fg.image != before).any()
+
+
+def test_animation_frames_match_the_oracle():
+    """'next' row 2: keyframe turntable (the shape of scene/helmet.json:55-92) driven through
+    rtx_scene_update_items, three frames, GPU vs oracle."""
+    from rustray_b200.animation import Animation
+    from rustray_b200.scene_loader import Item, SHAPE_MESH, Material, mat_identity
+    fs, cam, cfg = abi.load_fixture("monkey_gltf", samples=1, monte_carlo=0)
+    cam = abi.resize_camera(cam, 240, 135)
+    g, c = _pair(fs, 240, 135)
+    kf = lambda ry: {"rotation": {"x": -25.0, "y": ry, "z": 0.0}, "scale": {"x": 0.8, "y": 0.8, "z": 0.8}, "translation": {"x": 0.3, "y": 0.2, "z": 0.0}}
+    an = Animation({"fps": 25, "enabled": True, "keyframes": [{"time": 0, "objects": [{"name": "Suzanne", "transformation": kf(15.0)}]},
+                                                              {"time": 6000, "objects": [{"name": "Suzanne", "transformation": kf(375.0)}]}]})
+    items = [Item(id=0, name=n, shape=SHAPE_MESH, material=Material(), trans=mat_identity()) for n in fs.item_names]
+    seen = []
+    for frame in (0, 40, 110):
+        ups = an.updates_for_frame(items, frame)
+        assert len(ups) == 1
+        for r in (g, c):
+            r.update_items(ups)
+        fg, fc = g.start(cam, cfg), c.render(cam, cfg)
+        assert lsb_stats(fg.image, fc.image)[0] >= 0.999 and np.array_equal(fg.objects, fc.objects) and np.array_equal(fg.depth, fc.depth)
+        seen.append(fg.image.copy())
+    assert (seen[0] != seen[1]).any() and (seen[1] != seen[2]).any()
 
 
 def test_error_codes_instead_of_panics():

@@ -87,3 +87,42 @@ def test_json_config_beats_cli_and_nested_scenes():
     assert ids == sorted(ids) and len(set(ids)) == len(ids)
     assert len(sc.items) == 6 + 8                                  # room planes + spheres
     assert not sc.cam.is_default_cam()
+
+
+@needs_reference
+def test_gltf_loader_semantics():
+    """Scene::load_gltf (scene.rs:722-978): one de-indexed Mesh item per primitive, object id before material id,
+    file camera and KHR_lights_punctual lights (point intensity / 10), PBR factor mapping; .glb and .gltf agree."""
+    a = load_scene(["scene/models/monkey/monkey.gltf"], 320, 180, asset_root=REFERENCE)
+    b = load_scene(["scene/models/monkey/monkey.glb"], 320, 180, asset_root=REFERENCE)
+    it = a.items[0]
+    assert it.name == "Suzanne" and it.mesh.indices.shape == (15744, 3) and it.mesh.vertices.shape == (47232, 3)
+    assert np.array_equal(it.mesh.indices.reshape(-1), np.arange(47232))            # fully de-indexed
+    assert it.mesh.normals.shape == (47232, 3) and it.mesh.uvs.shape == (47232, 2)
+    assert [l.id for l in a.lights] == [1, 2] and (it.id, it.material.id) == (3, 4)  # lights, object id, then material id
+    m = it.material
+    assert m.reflectivity == 0.0 and m.roughness == pytest.approx(0.4 / (2 * np.pi), rel=1e-3) or m.roughness > 0
+    assert np.allclose(m.specular_color, m.base_color * np.float32(0.8))
+    assert not a.cam.is_default_cam() and a.cam.fov == pytest.approx(0.3996, abs=1e-3)
+    assert np.allclose(b.items[0].mesh.vertices, it.mesh.vertices, atol=1e-6)
+
+
+def test_animation_keyframe_interpolation():
+    """reference src/animation.rs: frame count, keyframe pick, linear interpolation, trans = T·Rz·Ry·Rx·S from identity
+    (the helmet.json turntable: rotation y 15 -> 375 degrees over 6 s at 25 fps)."""
+    from rustray_b200.animation import Animation
+    spec = {"fps": 25, "enabled": True, "keyframes": [
+        {"time": 0, "objects": [{"name": "helmet", "transformation": {"rotation": {"x": -25.0, "y": 15.0, "z": 0.0},
+                                                                        "scale": {"x": 1.25, "y": 1.25, "z": 1.25}, "translation": {"x": 0.3, "y": 0.2, "z": 0.0}}}]},
+        {"time": 6000, "objects": [{"name": "helmet", "transformation": {"rotation": {"x": -25.0, "y": 375.0, "z": 0.0},
+                                                                           "scale": {"x": 1.25, "y": 1.25, "z": 1.25}, "translation": {"x": 0.3, "y": 0.2, "z": 0.0}}}]}]}
+    an = Animation(spec)
+    assert an.has_animation() and an.frames_to_render() == 150
+    assert an.trans_for_frame(10, "nobody") is None
+    m0, m75 = an.trans_for_frame(0, "helmet"), an.trans_for_frame(75, "helmet")
+    assert np.allclose(m0[:3, 3], [0.3, 0.2, 0.0]) and np.allclose(np.linalg.det(m0[:3, :3].astype(np.float64)), 1.25 ** 3, rtol=1e-5)
+    # frame 75 = 3000 ms: rotation y = 15 + 180 degrees -> the rotation part is m0's with x and z columns mirrored about Y
+    ry = lambda d: np.array([[np.cos(np.radians(d)), 0, np.sin(np.radians(d))], [0, 1, 0], [-np.sin(np.radians(d)), 0, np.cos(np.radians(d))]])
+    rx = lambda d: np.array([[1, 0, 0], [0, np.cos(np.radians(d)), -np.sin(np.radians(d))], [0, np.sin(np.radians(d)), np.cos(np.radians(d))]])
+    assert np.allclose(m75[:3, :3], ry(195.0) @ rx(-25.0) * 1.25, atol=1e-5)
+    assert not Animation({"enabled": False}).has_animation() and not Animation(None).has_animation()
