@@ -791,7 +791,7 @@ int oracle_scene_create(const RtxSceneDesc* d, int /*device*/, RtxScene** out) {
         Item it; it.d = d->items[i];
         if (it.d.material < 0 || (uint32_t)it.d.material >= d->n_materials) { delete sc; g_err = "bad material index"; return RTX_E_INVALID; }
         if (it.d.shape == RTX_SHAPE_MESH && (it.d.mesh < 0 || (uint32_t)it.d.mesh >= d->n_meshes)) { delete sc; g_err = "bad mesh index"; return RTX_E_INVALID; }
-        if (it.d.tran_inverse[3] != 0.0f || it.d.tran_inverse[7] != 0.0f || it.d.tran_inverse[11] != 0.0f) { delete sc; g_err = "non-affine transform"; return RTX_E_NON_AFFINE; }
+        if (it.d.tran_inverse[3] != 0.0f || it.d.tran_inverse[7] != 0.0f || it.d.tran_inverse[11] != 0.0f || !(it.d.tran_inverse[15] > 0.5f && it.d.tran_inverse[15] < 2.0f)) { delete sc; g_err = "item transform is not affine"; return RTX_E_NON_AFFINE; }
         update_item(*sc, it);
         sc->items.push_back(it);
     }

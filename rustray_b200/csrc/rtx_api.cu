@@ -125,9 +125,11 @@ void fill_item(const RtxScene& sc, const RtxItem& s, DItem& d) {
     if (m.texture[RTX_TEX_ALPHA] >= 0) f |= IF_ALPHA_TEX;
     {   // identity + translation inverse (planes, spheres): the per-item ray transform degenerates to one add per axis
         const float* t = s.tran_inverse;
-        if (t[0] == 1.f && t[5] == 1.f && t[10] == 1.f && t[1] == 0.f && t[2] == 0.f && t[4] == 0.f && t[6] == 0.f && t[8] == 0.f && t[9] == 0.f)
+        if (t[0] == 1.f && t[5] == 1.f && t[10] == 1.f && t[15] == 1.f && t[1] == 0.f && t[2] == 0.f && t[4] == 0.f && t[6] == 0.f && t[8] == 0.f && t[9] == 0.f)
             f |= IF_TRANSLATION;
     }
+    d.inv_w = s.tran_inverse[15];
+    if (d.inv_w != 1.0f) f |= IF_DIV_W;
     d.id = s.id; d.material = (uint32_t)s.material;
     d.lo.w = s.radius; d.hi.w = c_alpha;
     d.flags = f;
@@ -336,7 +338,7 @@ int rtx_scene_create(const RtxSceneDesc* d, int device, RtxScene** out) {
         if (it.shape == RTX_SHAPE_MESH && (it.mesh < 0 || (uint32_t)it.mesh >= d->n_meshes)) return bail(RTX_E_INVALID, "item mesh index out of range");
         if (it.shape != RTX_SHAPE_MESH && it.shape != RTX_SHAPE_SPHERE) return bail(RTX_E_INVALID, "unknown shape kind");
         // Vector3::from_homogeneous(tran_inverse * dir).unwrap() needs w == 0 (src/shape/mod.rs:760)
-        if (it.tran_inverse[3] != 0.0f || it.tran_inverse[7] != 0.0f || it.tran_inverse[11] != 0.0f || it.tran_inverse[15] != 1.0f)
+        if (it.tran_inverse[3] != 0.0f || it.tran_inverse[7] != 0.0f || it.tran_inverse[11] != 0.0f || !(it.tran_inverse[15] > 0.5f && it.tran_inverse[15] < 2.0f))
             return bail(RTX_E_NON_AFFINE, "item transform is not affine");
     }
     for (uint32_t i = 0; i < d->n_materials; i++)
@@ -487,7 +489,7 @@ int rtx_scene_update_items(RtxScene* sc, const RtxItemXform* x, size_t n) {
     for (size_t i = 0; i < n; i++) {
         if (x[i].item_index >= sc->src_items.size()) return fail(RTX_E_INVALID, "item index out of range");
         const float* ti = x[i].tran_inverse;
-        if (ti[3] != 0.0f || ti[7] != 0.0f || ti[11] != 0.0f || ti[15] != 1.0f) return fail(RTX_E_NON_AFFINE, "item transform is not affine");
+        if (ti[3] != 0.0f || ti[7] != 0.0f || ti[11] != 0.0f || !(ti[15] > 0.5f && ti[15] < 2.0f)) return fail(RTX_E_NON_AFFINE, "item transform is not affine");
     }
     for (size_t i = 0; i < n; i++) {
         RtxItem& s = sc->src_items[x[i].item_index]; DItem& d = sc->h_items[x[i].item_index];
@@ -497,8 +499,10 @@ int rtx_scene_update_items(RtxScene* sc, const RtxItemXform* x, size_t n) {
             d.mat[r] = make_float4(s.trans[0 + r], s.trans[4 + r], s.trans[8 + r], s.trans[12 + r]);
         }
         const float* t = s.tran_inverse;
-        const bool tr = t[0] == 1.f && t[5] == 1.f && t[10] == 1.f && t[1] == 0.f && t[2] == 0.f && t[4] == 0.f && t[6] == 0.f && t[8] == 0.f && t[9] == 0.f;
+        const bool tr = t[0] == 1.f && t[5] == 1.f && t[10] == 1.f && t[15] == 1.f && t[1] == 0.f && t[2] == 0.f && t[4] == 0.f && t[6] == 0.f && t[8] == 0.f && t[9] == 0.f;
         d.flags = tr ? (d.flags | IF_TRANSLATION) : (d.flags & ~IF_TRANSLATION);
+        d.inv_w = t[15];
+        d.flags = (t[15] != 1.0f) ? (d.flags | IF_DIV_W) : (d.flags & ~IF_DIV_W);
     }
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(sc->items.p, sc->h_items.data(), sc->h_items.size() * sizeof(DItem), cudaMemcpyHostToDevice));

@@ -22,6 +22,7 @@ namespace rtx {
 enum : uint32_t {
     IF_MESH = 1u, IF_VISIBLE = 2u, IF_FLIP = 4u, IF_CAST_SHADOW = 8u, IF_REFL_ONLY = 16u, IF_BACKFACE = 32u,
     IF_SMOOTH = 64u, IF_HAS_NORMALS = 128u, IF_ALPHA_TEX = 256u, IF_ALPHA_POS = 512u, IF_ALPHA_LT1 = 1024u,
+    IF_DIV_W = 4096u,          // tran_inverse[3][3] != 1 (rounding of the cofactor inverse): points are divided by it, like from_homogeneous
     IF_TRANSLATION = 2048u     // tran_inverse is identity + translation: o' = o + t, d' = d (bit-identical to the general product)
 };
 
@@ -31,7 +32,7 @@ struct alignas(16) DItem {
     float4 lo;          // local AABB min, w = radius
     float4 hi;          // local AABB max, w = cached material alpha
     uint32_t flags, id, material, root;               // root = BLAS root node (mesh)
-    uint32_t n_faces, n_uv_faces, n_normal_faces, pad0;
+    uint32_t n_faces, n_uv_faces, n_normal_faces; float inv_w;   // inv_w = tran_inverse[3][3]: Point3::from_homogeneous divides by it
     uint32_t vert_off, idx_off, uv_off, uvidx_off;    // element offsets into the mesh arrays
     uint32_t nrm_off, nidx_off, pad1, pad2;
 };
@@ -104,6 +105,12 @@ __device__ __forceinline__ float3 xnormalize(float3 a) { float n = xnorm(a); ret
 // row r of an affine 3x4 (row = m[r][0..3]) times (x,y,z,w): ((m0*x + m1*y) + m2*z) + m3*w
 __device__ __forceinline__ float xrow(float4 r, float3 v, float w) { return xa(xa(xa(xm(r.x, v.x), xm(r.y, v.y)), xm(r.z, v.z)), xm(r.w, w)); }
 __device__ __forceinline__ float3 xform_point(const float4 m[3], float3 p) { return f3(xrow(m[0], p, 1.0f), xrow(m[1], p, 1.0f), xrow(m[2], p, 1.0f)); }
+// tran_inverse * point.to_homogeneous() -> Point3::from_homogeneous: w = m33 (affine), divide when it is not 1
+__device__ __forceinline__ float3 xform_point_w(const float4 m[3], float3 p, uint32_t flags, float w) {
+    float3 r = xform_point(m, p);
+    if (flags & IF_DIV_W) r = f3(xd(r.x, w), xd(r.y, w), xd(r.z, w));
+    return r;
+}
 __device__ __forceinline__ float3 xform_vec(const float4 m[3], float3 v) { return f3(xrow(m[0], v, 0.0f), xrow(m[1], v, 0.0f), xrow(m[2], v, 0.0f)); }
 
 // plain float3 helpers (shading; contraction allowed)
@@ -381,7 +388,7 @@ __device__ __forceinline__ void visit_item_closest(const SceneDev& S, uint32_t i
     const uint32_t flags = it->flags;
     if (!item_passes(flags, for_shadow, depth)) return;
     float4 inv[3] = {__ldg(&it->inv[0]), __ldg(&it->inv[1]), __ldg(&it->inv[2])};
-    const float3 lo3 = xform_point(inv, o), ld3 = xform_vec(inv, d);
+    const float3 lo3 = xform_point_w(inv, o, flags, it->inv_w), ld3 = xform_vec(inv, d);
     const float4 lo = __ldg(&it->lo), hi = __ldg(&it->hi);
     const bool solid = item_solid(flags, for_shadow);
     float key;
@@ -448,7 +455,7 @@ __device__ __forceinline__ void cand_consider(const SceneDev& S, uint32_t ii, fl
     const uint32_t flags = it->flags;
     if (!item_passes(flags, true, depth)) return;
     float4 inv[3] = {__ldg(&it->inv[0]), __ldg(&it->inv[1]), __ldg(&it->inv[2])};
-    const float3 lo3 = xform_point(inv, o), ld3 = xform_vec(inv, d);
+    const float3 lo3 = xform_point_w(inv, o, flags, it->inv_w), ld3 = xform_vec(inv, d);
     const float4 lo = __ldg(&it->lo), hi = __ldg(&it->hi);
     float key;
     if (!aabb_cast(f3(lo.x, lo.y, lo.z), f3(hi.x, hi.y, hi.z), lo3, ld3, false, key)) return;
@@ -500,7 +507,7 @@ __device__ __forceinline__ bool item_shadow_test(const SceneDev& S, uint32_t ii,
                                                  TravStats& st) {
     const DItem* it = S.items + ii;
     float4 inv[3] = {__ldg(&it->inv[0]), __ldg(&it->inv[1]), __ldg(&it->inv[2])};
-    const float3 lo3 = xform_point(inv, o), ld3 = xform_vec(inv, d);
+    const float3 lo3 = xform_point_w(inv, o, it->flags, it->inv_w), ld3 = xform_vec(inv, d);
     if (it->flags & IF_MESH) {
         bool h = traverse_mesh<MODE, STATS>(S.nodes, S.tris, it->root, lo3, ld3, limit, mh, st);
         if (MODE == TM_CLOSEST && h) hf = mh.back;
@@ -549,7 +556,7 @@ __device__ __forceinline__ void trace_shadow_fast(const SceneDev& S, float3 o, f
             const uint32_t ii = cl.item[k];
             const DItem* it = S.items + ii;
             float4 inv[3] = {__ldg(&it->inv[0]), __ldg(&it->inv[1]), __ldg(&it->inv[2])};
-            const float3 lo3 = xform_point(inv, o), ld3 = xform_vec(inv, d);
+            const float3 lo3 = xform_point_w(inv, o, it->flags, it->inv_w), ld3 = xform_vec(inv, d);
             int cls;                                                   // 0 none, 1 hit <= len, 2 only beyond len
             MeshHit mh;
             if (it->flags & IF_MESH) {
@@ -674,7 +681,7 @@ __device__ __forceinline__ void lane_leaf(Lane& L, uint2* __restrict__ stack, co
         lo3 = f3(xa(L.w.o.x, r0.w), xa(L.w.o.y, r1.w), xa(L.w.o.z, r2.w)); ld3 = L.w.d;
     } else {
         float4 inv[3] = {__ldg(&it->inv[0]), __ldg(&it->inv[1]), __ldg(&it->inv[2])};
-        lo3 = xform_point(inv, L.w.o); ld3 = xform_vec(inv, L.w.d);
+        lo3 = xform_point_w(inv, L.w.o, flags, it->inv_w); ld3 = xform_vec(inv, L.w.d);
     }
     const float4 lo = __ldg(&it->lo), hi = __ldg(&it->hi);
     const bool solid = item_solid(flags, for_shadow);
@@ -717,7 +724,7 @@ __device__ __forceinline__ float3 ld3(const float* p, uint32_t i) { return f3(__
 
 // area-ratio weights of Mesh::get_uv / get_normal (reference src/shape/mesh.rs:105-161, 204-259)
 __device__ __forceinline__ void area_weights(const SceneDev& S, const DItem& it, float3 hit, uint32_t f_id, float w[3]) {
-    const float3 hl = xform_point(it.inv, hit);
+    const float3 hl = xform_point_w(it.inv, hit, it.flags, it.inv_w);
     const uint32_t* fi = S.idx + it.idx_off + 3 * (size_t)f_id;
     const float3 a = ld3(S.verts + it.vert_off, __ldg(fi)), b = ld3(S.verts + it.vert_off, __ldg(fi + 1)), c = ld3(S.verts + it.vert_off, __ldg(fi + 2));
     const float3 f1 = xsub(a, hl), f2 = xsub(b, hl), f3_ = xsub(c, hl);
@@ -728,7 +735,7 @@ __device__ __forceinline__ void area_weights(const SceneDev& S, const DItem& it,
 __device__ __forceinline__ void item_get_uv(const SceneDev& S, const DItem& it, float3 hit, uint32_t face_id, float& u, float& v) {
     const float PI = 3.14159265358979323846f;
     if (!(it.flags & IF_MESH)) {                                  // sphere.rs:69-99
-        const float3 hl = xform_point(it.inv, hit);
+        const float3 hl = xform_point_w(it.inv, hit, it.flags, it.inv_w);
         const float theta = atan2f(-hl.z, hl.x);
         u = (theta + PI) / (2.0f * PI);
         const float phi = acosf((-hl.y) / it.lo.w);
@@ -750,7 +757,7 @@ __device__ __forceinline__ void item_get_uv(const SceneDev& S, const DItem& it, 
 __device__ __forceinline__ float3 hit_normal(const SceneDev& S, const DItem& it, float3 o, float3 d, float t, uint32_t prim, uint32_t hflags,
                                              uint32_t& face_id) {
     if (!(it.flags & IF_MESH)) {
-        const float3 lo3 = xform_point(it.inv, o), ld = xform_vec(it.inv, d);
+        const float3 lo3 = xform_point_w(it.inv, o, it.flags, it.inv_w), ld = xform_vec(it.inv, d);
         float3 n = xnormalize(xadd(lo3, xscale(ld, t)));
         if ((hflags & HF_INSIDE) && S.ball_flip_inside) n = xneg(n);
         face_id = 0;
