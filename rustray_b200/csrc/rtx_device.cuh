@@ -14,6 +14,15 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef RTX_SHADE_NOINLINE
+#define RTX_SHADE_NOINLINE 0
+#endif
+#if RTX_SHADE_NOINLINE
+#define RTX_SHADE_INLINE __noinline__      // keeps shade_kernel's code small enough for the instruction cache
+#else
+#define RTX_SHADE_INLINE __forceinline__
+#endif
+
 namespace rtx {
 
 // ------------------------------------------------------------------------------------------------
@@ -732,7 +741,7 @@ __device__ __forceinline__ void area_weights(const SceneDev& S, const DItem& it,
     w[0] = xd(xnorm(xcross(f2, f3_)), area); w[1] = xd(xnorm(xcross(f3_, f1)), area); w[2] = xd(xnorm(xcross(f1, f2)), area);
 }
 
-__device__ __forceinline__ void item_get_uv(const SceneDev& S, const DItem& it, float3 hit, uint32_t face_id, float& u, float& v) {
+__device__ RTX_SHADE_INLINE void item_get_uv(const SceneDev& S, const DItem& it, float3 hit, uint32_t face_id, float& u, float& v) {
     const float PI = 3.14159265358979323846f;
     if (!(it.flags & IF_MESH)) {                                  // sphere.rs:69-99
         const float3 hl = xform_point_w(it.inv, hit, it.flags, it.inv_w);
@@ -803,7 +812,7 @@ __device__ __forceinline__ uint32_t tex_wrap(float val, uint32_t bound) {
 }
 __device__ __forceinline__ float lerp1(float a, float b, float f) { return xa(a, xm(f, xs(b, a))); }
 __device__ __forceinline__ float4 lerp4(float4 a, float4 b, float f) { return make_float4(lerp1(a.x, b.x, f), lerp1(a.y, b.y, f), lerp1(a.z, b.z, f), lerp1(a.w, b.w, f)); }
-__device__ __forceinline__ float4 tex_interpolate(const SceneDev& S, const DTex& t, float xf, float yf) {
+__device__ RTX_SHADE_INLINE float4 tex_interpolate(const SceneDev& S, const DTex& t, float xf, float yf) {
     float x = xm(xf, (float)t.w), y = xm(yf, (float)t.h);
     if (x < 0.0f) x = xa(x, (float)t.w);
     if (y < 0.0f) y = xa(y, (float)t.h);
@@ -856,7 +865,7 @@ __device__ __forceinline__ float fresnel(float3 incident, float3 normal, float i
     const float r_p = ((eta_i * cos_i) - (eta_t * cos_t)) / ((eta_i * cos_i) + (eta_t * cos_t));
     return (r_s * r_s + r_p * r_p) / 2.0f;
 }
-__device__ __forceinline__ float3 jitter(float3 dir, float spread, uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t path, uint32_t slot) {
+__device__ RTX_SHADE_INLINE float3 jitter(float3 dir, float spread, uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t path, uint32_t slot) {
     const float PI = 3.14159265358979323846f;
     if (spread <= 0.0f) return dir;
     const float3 b3 = norm3(dir);
