@@ -237,6 +237,16 @@ def run_ours(args):
     e2e_rays = allsum(e2e_rays)
     e2e_val = e2e_rays / e2e_s / 1e6
 
+    # ---- informational: opt-in RTX_OPT_SKIP_ZERO_SHADOW (not the headline: the headline traces every reference ray) ----
+    cfg_skip = abi.RtxConfig(); C.memmove(C.byref(cfg_skip), C.byref(cfg), C.sizeof(cfg)); cfg_skip.debug_flags = 4
+    skip_ms, skip_st = 0.0, None
+    for i in range(4):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); skip_st = sr.render_local(cam, cfg_skip); sr.gather(); e1.record(); torch.cuda.synchronize()
+        if i > 0:
+            skip_ms += allmax(e0.elapsed_time(e1)) / 3
+
     if rank == 0:
         peak, peak_src = measured_peaks()
         dom = "closest_kernel" if closest_ms >= shadow_ms else "shadow_any_kernel"
@@ -271,6 +281,8 @@ def run_ours(args):
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": 1e3 * e2e_s / args.steps},
                 "gpu_launches": int(launches), "roofline": roofline, "rays_per_step": rays_all / args.steps,
+                "opt_skip_zero_shadow": {"ms_per_frame": skip_ms, "rays_skipped_rank0": int(skip_st.rays_shadow_skipped),
+                                         "note": "opt-in flag, image-identical; informational, not part of value/e2e"},
                 "ms_per_frame": ms_per_step}
         if cpu is not None:
             line["cpu_baseline"] = cpu

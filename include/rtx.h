@@ -142,6 +142,10 @@ typedef struct RtxConfig {
 } RtxConfig;
 
 #define RTX_DEBUG_COLLECT_STATS  1u   /* count node visits / primitive tests per ray (slower)        */
+#define RTX_OPT_SKIP_ZERO_SHADOW 4u   /* opt-in: a shadow ray whose light contribution is exactly (0,0,0) cannot change the
+                                         frame and is not traced; still counted in rays_shadow (the reference calls trace
+                                         for it) and reported in rays_shadow_skipped.  Off by default: the bench traces
+                                         every ray the reference traces.                                              */
 #define RTX_DEBUG_ORDERED_SHADOW 2u   /* shadow rays: literal "closest hit of every item in bbox
                                          order" walk instead of the equivalent two-phase any-hit     */
 
@@ -166,6 +170,7 @@ typedef struct RtxStats {
     float shadow_ms;       /* CUDA events, sum over shadow kernel launches                          */
     float shade_ms;        /* device_ms - closest_ms - shadow_ms (raygen, shade, resolve, gaps)     */
     uint64_t h2d_bytes, d2h_bytes;
+    uint64_t rays_shadow_skipped;   /* RTX_OPT_SKIP_ZERO_SHADOW: shadow rays not traced (included in rays_shadow) */
 } RtxStats;
 
 typedef struct RtxRay { float origin[3]; float dir[3]; } RtxRay;

@@ -665,7 +665,7 @@ int rtx_render_frame_device(RtxScene* sc, const RtxCamera* cam, const RtxConfig*
             so.child = RayQ{C.o + off, C.d + off, C.m + off};
             so.child_cap = d + 1 <= L ? sc->level_cap - off : 0;
             so.child_count = ctr + 2;
-            so.shadow = SQ; so.shadow_cap = sc->shadow_cap; so.shadow_count = ctr + 3; so.overflow = sc->overflow.p;
+            so.shadow = SQ; so.shadow_cap = sc->shadow_cap; so.shadow_count = ctr + 3; so.overflow = sc->overflow.p; so.skipped = sc->overflow.p + 2;
             const int blocks = (int)std::min<uint32_t>((n + kShadeBlock - 1) / kShadeBlock, (uint32_t)sc->sm_count * 16);
             shade_kernel<<<blocks, kShadeBlock, 0, st>>>(sc->dev, F, Q, q_base, n, sc->hits.p, so);
             launches++;
@@ -712,6 +712,10 @@ int rtx_render_frame_device(RtxScene* sc, const RtxCamera* cam, const RtxConfig*
         stats->rays_closest = rays_closest; stats->rays_shadow = rays_shadow; stats->primary_samples = primary;
         stats->kernel_launches = launches; stats->waves = waves; stats->batches = batches;
         stats->h2d_bytes = h2d; stats->d2h_bytes = (uint64_t)waves * 16;
+        {
+            uint32_t ovf[4]; CU(cudaMemcpy(ovf, sc->overflow.p, 16, cudaMemcpyDeviceToHost));
+            stats->rays_shadow_skipped = ovf[2]; stats->rays_shadow += ovf[2];
+        }
         if (want_stats) {
             Counters c; CU(cudaMemcpy(&c, sc->counters.p, sizeof(c), cudaMemcpyDeviceToHost));
             stats->node_visits[0] = c.node_visits[0]; stats->node_visits[1] = c.node_visits[1];

@@ -286,6 +286,7 @@ struct ShadeOut {
     RayQ child; uint32_t child_cap; uint32_t* child_count;      // level d+1 queue
     ShadowQ shadow; uint32_t shadow_cap; uint32_t* shadow_count;
     uint32_t* overflow;                                         // set to 1 if a queue would overflow (never, by construction)
+    uint32_t* skipped;                                          // RTX_OPT_SKIP_ZERO_SHADOW: count of untraced zero-contribution shadow rays
 };
 
 #ifndef RTX_SHADE_MIN_BLOCKS
@@ -333,8 +334,17 @@ __global__ void __launch_bounds__(kShadeBlock, RTX_SHADE_MIN_BLOCKS) shade_kerne
             const bool has_uv = mat.any_texture != 0;
             float u = 0.0f, v = 0.0f;
             if (has_uv) item_get_uv(S, item, hit_point, face_id, u, v);
+            // all eight texture lookups in ONE rolled loop (one copy of the nearest / bilinear fetch code instead of eight:
+            // the kernel otherwise outgrows the instruction cache)
+            float4 texc[8]; uint32_t tex_mask = 0;
+#pragma unroll 1
+            for (int tt = 0; tt < 8; tt++) {
+                float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (get_tex_color(S, mat, has_uv, u, v, tt, c4)) tex_mask |= 1u << tt;
+                texc[tt] = c4;
+            }
             float4 tc;
-            if (get_tex_color(S, mat, has_uv, u, v, 3 /*Normal*/, tc)) {          // :757-784
+            if ((tex_mask >> 3) & 1u) { tc = texc[3];                                  // Normal :757-784
                 float3 tangent = xcross(normal, f3(0, 1, 0));
                 if (xnorm(tangent) <= 0.0001f) tangent = xcross(normal, f3(0, 0, 1));
                 tangent = xnormalize(tangent);
@@ -346,24 +356,24 @@ __global__ void __launch_bounds__(kShadeBlock, RTX_SHADE_MIN_BLOCKS) shade_kerne
                                                xa(xa(xm(tangent.y, nm.x), xm(bitangent.y, nm.y)), xm(normal.y, nm.z)),
                                                xa(xa(xm(tangent.z, nm.x), xm(bitangent.z, nm.y)), xm(normal.z, nm.z))));
             }
-            const bool has_rough = get_tex_color(S, mat, has_uv, u, v, 5 /*Roughness*/, tc);   // :787-798
+            const bool has_rough = (tex_mask >> 5) & 1u; tc = texc[5];                 // Roughness :787-798
             if (F.monte_carlo && mat.monte_carlo && (mat.roughness > 0.0f || has_rough)) {
                 float roughness = mat.roughness;
                 if (has_rough) roughness = (1.0f / PI / 2.0f) * tc.x;
                 surface_normal = jitter(surface_normal, roughness, F.mc_seed, pixel, sample, path, 0);
             }
             float4 ambient_color = make_float4(mat.ambient[0], mat.ambient[1], mat.ambient[2], 1.0f);   // :801-803
-            if (get_tex_color(S, mat, has_uv, u, v, 1 /*AmbientEmissive*/, tc)) { ambient_color.x *= tc.x; ambient_color.y *= tc.y; ambient_color.z *= tc.z; }
+            if ((tex_mask >> 1) & 1u) { tc = texc[1]; ambient_color.x *= tc.x; ambient_color.y *= tc.y; ambient_color.z *= tc.z; }
             base_color = make_float4(mat.base[0], mat.base[1], mat.base[2], 1.0f);
-            if (get_tex_color(S, mat, has_uv, u, v, 0 /*Base*/, tc)) { base_color.x *= tc.x; base_color.y *= tc.y; base_color.z *= tc.z; base_color.w *= tc.w; }
+            if (tex_mask & 1u) { tc = texc[0]; base_color.x *= tc.x; base_color.y *= tc.y; base_color.z *= tc.z; base_color.w *= tc.w; }
             specular_color = make_float4(mat.specular[0], mat.specular[1], mat.specular[2], 1.0f);
-            if (get_tex_color(S, mat, has_uv, u, v, 2 /*Specular*/, tc)) { specular_color.x *= tc.x; specular_color.y *= tc.y; specular_color.z *= tc.z; }
+            if ((tex_mask >> 2) & 1u) { tc = texc[2]; specular_color.x *= tc.x; specular_color.y *= tc.y; specular_color.z *= tc.z; }
             float alpha = mat.alpha * base_color.w;                                // :806-811
-            if (get_tex_color(S, mat, has_uv, u, v, 4 /*Alpha*/, tc)) alpha *= tc.x;
+            if ((tex_mask >> 4) & 1u) alpha *= texc[4].x;
 
             const float kr = fresnel(d, surface_normal, mat.refraction_index);   // :925
             float reflectivity = mat.reflectivity;                                // :928-933
-            if (get_tex_color(S, mat, has_uv, u, v, 7 /*Reflectivity*/, tc)) reflectivity = tc.x;
+            if ((tex_mask >> 7) & 1u) reflectivity = texc[7].x;
             const bool can_recurse = depth <= F.max_recursion;
             const bool reflect_on = reflectivity > 0.0f && can_recurse;           // :938
             bool trans_exists = false;
@@ -373,7 +383,7 @@ __global__ void __launch_bounds__(kShadeBlock, RTX_SHADE_MIN_BLOCKS) shade_kerne
             const float kt = trans_exists ? ((kr < 1.0f ? (1.0f - kr) : 1.0f) * (1.0f - alpha)) : 0.0f;
             const float fog = fminf(F.fog_density * hit_dist, 1.0f);              // :978-982
             float ao = 1.0f;
-            if (get_tex_color(S, mat, has_uv, u, v, 6 /*AmbientOcclusion*/, tc)) ao = tc.x;   // :985-991
+            if ((tex_mask >> 6) & 1u) ao = texc[6].x;                                  // :985-991
             const float thru = wgt * ao * (1.0f - fog);
             coef_d = thru * a * (1.0f - reflectivity);
             constant = f3(wgt * (ao * fog * F.fog_color[0] + ambient_color.x), wgt * (ao * fog * F.fog_color[1] + ambient_color.y),
@@ -419,7 +429,9 @@ __global__ void __launch_bounds__(kShadeBlock, RTX_SHADE_MIN_BLOCKS) shade_kerne
                        (L.color[1] * (specular_color.y * light_power + base_color.y * dot_light)) * intensity,
                        (L.color[2] * (specular_color.z * light_power + base_color.z * dot_light)) * intensity);
                 c = c * coef_d;
-                if (recv_shadow) {
+                const bool zero = (F.debug_flags & 4u) && c.x == 0.0f && c.y == 0.0f && c.z == 0.0f;
+                if (recv_shadow && zero) atomicAdd(out.skipped, 1u);            // opt-in: cannot change the frame
+                else if (recv_shadow) {
                     emit = true;
                     sdir = dtl;
                     if (F.monte_carlo && mat_mc) sdir = jitter(sdir, shadow_softness, F.mc_seed, pixel, sample, path, 2 + 2 * li);

@@ -215,6 +215,19 @@ def test_update_items_and_lights_between_frames():
         assert (fg.image != before).any()
 
 
+def test_opt_skip_zero_contribution_shadow_rays_is_image_neutral():
+    """RTX_OPT_SKIP_ZERO_SHADOW (opt-in, off in the bench): shadow rays whose contribution is exactly zero are not traced;
+    ray totals (as the reference counts them) and every output buffer stay identical."""
+    for name in ("c2_floor_monkey", "room_spheres"):
+        fs, cam, cfg = abi.load_fixture(name, samples=2, monte_carlo=0)
+        cam = abi.resize_camera(cam, 320, 180)
+        g = RendererManager(320, 180, fs)
+        a = g.start(cam, cfg); ia, oa, sa = a.image.copy(), a.objects.copy(), (a.stats.rays_closest, a.stats.rays_shadow)
+        b = g.start(cam, clone_cfg(cfg, debug_flags=4))
+        assert (b.stats.rays_closest, b.stats.rays_shadow) == sa and b.stats.rays_shadow_skipped > 0.1 * sa[1]
+        assert lsb_stats(ia, b.image)[0] >= 0.9999 and np.array_equal(oa, b.objects)
+
+
 def test_animation_frames_match_the_oracle():
     """'next' row 2: keyframe turntable (the shape of scene/helmet.json:55-92) driven through
     rtx_scene_update_items, three frames, GPU vs oracle."""
