@@ -80,7 +80,7 @@ def soup_scene(n_triangles: int = 10_000_000, n_spheres: int = 1000, cells: int 
     sc.lights.append(Light(sc.get_next_id(), "d", np.zeros(3, dtype=F), np.array([0.3, -1.0, -0.5], dtype=F),
                            np.array([1, 1, 1], dtype=F), 0.5, math.pi / 2, LIGHT_DIRECTIONAL))
     sc.cam = Camera()
-    sc.cam.eye_pos = np.array([0.0, e * 0.6, e * 2.6], dtype=F)
+    sc.cam.eye_pos = np.array([0.0, e * 0.6, e * 3.2], dtype=F)
     d = -sc.cam.eye_pos
     sc.cam.dir = (d / np.linalg.norm(d)).astype(F)
     sc.cam.fov = to_radians(60.0)

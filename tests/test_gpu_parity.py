@@ -252,6 +252,44 @@ def test_animation_frames_match_the_oracle():
     assert (seen[0] != seen[1]).any() and (seen[1] != seen[2]).any()
 
 
+def test_degenerate_inputs():
+    """Empty scene, 1x1 frame, no lights / all lights disabled, a 20 km ground plane (scene/floor_reflective.json shape),
+    rtx_scene_set_lights between frames."""
+    import ctypes
+    from rustray_b200.scene_loader import Scene, Item, Material, Light, SHAPE_SPHERE, SHAPE_MESH, LIGHT_POINT, mat_translation, mat_identity
+    empty = Scene(".")
+    empty.cam.init(17, 9)
+    fs, cam, cfg = scene_to_abi(empty)
+    g, c = _pair(fs, 17, 9)
+    fg, fc = g.start(cam, cfg), c.render(cam, cfg)
+    assert (fg.image[..., :3] == 0).all() and (fg.objects == 0).all() and np.isnan(fg.normals).all() and fg.stats.rays_shadow == 0
+    assert fg.stats.rays_closest == fc.stats.rays_closest == 17 * 9
+    assert g.trace([[0, 0, 0]], [[0, 0, -1]])[0]["t"] < 0
+
+    sc = Scene(".")
+    m = Material(id=1); m.reflectivity = 0.8; m.roughness = 0.015; m.base_color = np.array([0.2, 0.2, 0.2], dtype=np.float32)
+    sc.items.append(Item(id=2, name="ground", shape=SHAPE_MESH, material=m, trans=mat_identity(),
+                         mesh=synthetic.quad_mesh((-10000, 0, 10000), (10000, 0, 10000), (10000, 0, -10000), (-10000, 0, -10000))))
+    m2 = Material(id=3); m2.alpha = 0.4; m2.refraction_index = 1.4
+    sc.items.append(Item(id=4, name="ball", shape=SHAPE_SPHERE, material=m2, trans=mat_translation(0.0, 1.0, -6.0), radius=1.0))
+    sc.cam.eye_pos = np.array([0, 1.5, 0], dtype=np.float32)
+    for w, h in ((1, 1), (96, 54)):
+        sc.cam.init(w, h)
+        sc.lights = []
+        fs, cam, cfg = scene_to_abi(sc)
+        g, c = _pair(fs, w, h)
+        fg, fc = g.start(cam, cfg), c.render(cam, cfg)                      # no lights at all: no shadow kernel launches
+        assert fg.stats.rays_shadow == 0 and np.array_equal(fg.objects, fc.objects) and lsb_stats(fg.image, fc.image)[0] == 1.0
+        lights = [abi.RtxLight(1, 9, LIGHT_POINT, abi.c_f3(3, 6, -2), abi.c_f3(0, -1, 0), abi.c_f3(1, 1, 1), 120.0, 1.0),
+                  abi.RtxLight(0, 10, LIGHT_POINT, abi.c_f3(-3, 6, -2), abi.c_f3(0, -1, 0), abi.c_f3(1, 0, 0), 500.0, 1.0)]   # second one disabled
+        arr = (abi.RtxLight * 2)(*lights)
+        for r, fn in ((g, g._lib.rtx_scene_set_lights), (c, c._lib.oracle_scene_set_lights)):
+            assert fn(r._h, arr, 2) == 0
+        fg, fc = g.start(cam, cfg), c.render(cam, cfg)
+        assert fg.stats.rays_shadow == fc.stats.rays_shadow > 0 and fg.stats.rays_closest == fc.stats.rays_closest
+        assert np.array_equal(fg.objects, fc.objects) and np.array_equal(fg.depth, fc.depth) and lsb_stats(fg.image, fc.image)[0] >= 0.999
+
+
 def test_error_codes_instead_of_panics():
     fs, cam, cfg = abi.load_fixture("c1_spheres")
     g = RendererManager(16, 16, fs)

@@ -19,7 +19,7 @@ print("per ray: closest nodes %.1f tris %.1f | shadow nodes %.1f tris %.1f | ite
     s.node_visits[0] / s.rays_closest, s.tri_tests[0] / s.rays_closest, s.node_visits[1] / max(1, s.rays_shadow), s.tri_tests[1] / max(1, s.rays_shadow),
     s.item_tests / (s.rays_closest + s.rays_shadow)))
 bc = (s.node_visits[0] * 80 + s.tri_tests[0] * 48) / s.rays_closest; bs = (s.node_visits[1] * 80 + s.tri_tests[1] * 48) / max(1, s.rays_shadow)
-for i in range(3):
+for i in range(int(os.environ.get("C5_FRAMES", "3"))):
     t = time.time(); f = g.start(cam, cfg); dt = time.time() - t; s = f.stats
     rays = s.rays_closest + s.rays_shadow
     print("frame %d: wall %.2fs device %.1f ms closest %.1f ms shadow %.1f ms | rays %.1fM+%.1fM -> %.0f Mrays/s | closest %.0f GB/s shadow %.0f GB/s algorithmic | waves %d" % (
