@@ -161,7 +161,11 @@ void append_nodes(std::vector<float4>& out, const WideBvh& bvh, uint32_t node_of
 
 int build_tlas(RtxScene& sc, std::vector<float4>& tlas_nodes, std::vector<uint32_t>& tlas_prims) {
     std::vector<Aabb3> boxes(sc.h_items.size());
-    for (size_t i = 0; i < sc.h_items.size(); i++) item_world_box(sc.h_items[i], boxes[i]);
+    for (size_t i = 0; i < sc.h_items.size(); i++) {
+        item_world_box(sc.h_items[i], boxes[i]);
+        sc.h_items[i].wlo = make_float4(boxes[i].lo[0], boxes[i].lo[1], boxes[i].lo[2], 0.f);
+        sc.h_items[i].whi = make_float4(boxes[i].hi[0], boxes[i].hi[1], boxes[i].hi[2], 0.f);
+    }
     WideBvh bvh; build_wide_bvh(boxes.data(), (uint32_t)boxes.size(), bvh);
     if (bvh.max_depth > 6) return fail(RTX_E_INVALID, "TLAS too deep for the traversal stack");
     tlas_nodes.clear();
@@ -192,7 +196,11 @@ void refresh_dev(RtxScene& sc) {
     if (!sc.overflow.p) sc.overflow.alloc(4);
     D.dbg = sc.overflow.p + 1;
     D.any_alpha_tex = 0u;
-    D.flat_items = (!sc.h_items.empty() && sc.h_items.size() <= 24 && getenv("RTX_FLAT_ITEMS")) ? ((1u << sc.h_items.size()) - 1u) : 0u;   // measured slower than the 1-node TLAS (it prunes item visits)
+    {
+        // few items: walk the item list directly (each item pre-culled by its padded world box) instead of a TLAS node test
+        uint32_t lim = 0; if (const char* e = getenv("RTX_FLAT_ITEMS")) lim = (uint32_t)atoi(e);   // off: measured slower than the one-node TLAS
+        D.flat_items = (!sc.h_items.empty() && sc.h_items.size() <= std::min(lim, 24u)) ? ((1u << sc.h_items.size()) - 1u) : 0u;
+    }
     for (const DItem& it : sc.h_items) if (it.flags & IF_ALPHA_TEX) D.any_alpha_tex = 1u;
 }
 
@@ -505,14 +513,14 @@ int rtx_scene_update_items(RtxScene* sc, const RtxItemXform* x, size_t n) {
         d.flags = (t[15] != 1.0f) ? (d.flags | IF_DIV_W) : (d.flags & ~IF_DIV_W);
     }
     CU(cudaDeviceSynchronize());
-    CU(cudaMemcpy(sc->items.p, sc->h_items.data(), sc->h_items.size() * sizeof(DItem), cudaMemcpyHostToDevice));
     if (!sc->h_items.empty()) {                                           // Scene::update rebuilds the item BVH (scene.rs:1681-1687)
         std::vector<float4> tn; std::vector<uint32_t> tp;
-        int rc = build_tlas(*sc, tn, tp); if (rc) return rc;
+        int rc = build_tlas(*sc, tn, tp); if (rc) return rc;              // also refreshes the items' world boxes
         if (tn.size() / 5 > sc->tlas_cap) return fail(RTX_E_INVALID, "TLAS capacity exceeded");
         CU(cudaMemcpy(sc->nodes.p + (size_t)sc->n_blas_nodes * 5, tn.data(), tn.size() * sizeof(float4), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(sc->tlas_prims.p, tp.data(), tp.size() * 4, cudaMemcpyHostToDevice));
     }
+    CU(cudaMemcpy(sc->items.p, sc->h_items.data(), sc->h_items.size() * sizeof(DItem), cudaMemcpyHostToDevice));
     return RTX_OK;
 }
 

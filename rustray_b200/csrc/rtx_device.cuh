@@ -44,6 +44,7 @@ struct alignas(16) DItem {
     uint32_t n_faces, n_uv_faces, n_normal_faces; float inv_w;   // inv_w = tran_inverse[3][3]: Point3::from_homogeneous divides by it
     uint32_t vert_off, idx_off, uv_off, uvidx_off;    // element offsets into the mesh arrays
     uint32_t nrm_off, nidx_off, pad1, pad2;
+    float4 wlo, whi;    // padded world-space AABB (the TLAS leaf box): cheap pre-cull when the item list is walked without a TLAS
 };
 
 struct alignas(16) DMaterial {
@@ -684,6 +685,17 @@ __device__ __forceinline__ void lane_leaf(Lane& L, uint2* __restrict__ stack, co
     const DItem* it = S.items + ii;
     const uint32_t flags = it->flags;
     if (!item_passes(flags, for_shadow, depth)) return;
+    if (S.flat_items) {                                                   // no TLAS node above this item: conservative world-box pre-cull
+        const float4 wl = __ldg(&it->wlo), wh = __ldg(&it->whi);
+        const float ax = (wl.x - L.r.o.x) * L.r.idir.x, bx = (wh.x - L.r.o.x) * L.r.idir.x;
+        const float ay = (wl.y - L.r.o.y) * L.r.idir.y, by = (wh.y - L.r.o.y) * L.r.idir.y;
+        const float az = (wl.z - L.r.o.z) * L.r.idir.z, bz = (wh.z - L.r.o.z) * L.r.idir.z;
+        const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+        const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+        // closest: nothing beyond the best hit matters; any-hit: every candidate must be seen (order rule), no clipping
+        const float lim = (MODE == UT_CLOSEST) ? L.tmax : 3.402823466e+38f;
+        if (!(tn * 0.999999f <= fminf(tf * 1.000001f, lim))) return;
+    }
     float3 lo3, ld3;
     if (flags & IF_TRANSLATION) {                                         // ((1*x + 0*y) + 0*z) + t*1 == x + t for finite inputs
         const float4 r0 = __ldg(&it->inv[0]), r1 = __ldg(&it->inv[1]), r2 = __ldg(&it->inv[2]);
