@@ -38,6 +38,8 @@ extern "C" {
 #define RTX_E_NON_AFFINE   -4   /* item transform is not affine (reference would panic in
                                    Vector3::from_homogeneous, src/shape/mod.rs:760)          */
 #define RTX_E_EMPTY_MESH   -5   /* mesh with 0 triangles (parry TriMesh::new panics)         */
+#define RTX_E_CANCELLED    -6   /* rtx_render_stop was called while the frame was in flight  */
+#define RTX_E_BUSY         -7   /* a frame is already in flight on this scene handle         */
 
 /* TextureType order — reference src/shape/mod.rs:633-643 */
 enum {
@@ -212,6 +214,17 @@ int rtx_scene_set_lights(RtxScene* scene, const RtxLight* lights, uint32_t n_lig
 int rtx_render_frame(RtxScene* scene, const RtxCamera* cam, const RtxConfig* cfg,
                      uint8_t* rgba, float* normals, float* depth, uint32_t* object_ids,
                      RtxStats* stats);
+
+/* Non-blocking variant for the GUI path: RendererManager::start returns at once and the window polls
+ * is_running / is_done / get_rendered_pixels and may call stop (reference src/renderer.rs:105-172, 174-231).
+ * rtx_render_frame_async starts the frame on a worker thread (same HOST buffers as rtx_render_frame, they must stay
+ * valid until done); rtx_render_poll reports progress — pixels_rendered counts pixels whose samples have all been
+ * issued, and equals width*height exactly when the frame is complete and the buffers are filled; `result` receives the
+ * frame's return code once it is no longer running.  rtx_render_stop cancels between waves and joins the worker. */
+int rtx_render_frame_async(RtxScene* scene, const RtxCamera* cam, const RtxConfig* cfg,
+                           uint8_t* rgba, float* normals, float* depth, uint32_t* object_ids);
+int rtx_render_poll(RtxScene* scene, uint64_t* pixels_rendered, int* running, int* done, int* result, RtxStats* stats);
+int rtx_render_stop(RtxScene* scene);
 
 /* Same frame, DEVICE output buffers (same layouts) on the scene's device, restricted to the
  * pixels of `shard` (NULL = whole frame); pixels of other ranks are left untouched.

@@ -10,6 +10,7 @@
 // that keeps every queue below 3*CHUNK without ever dropping or re-queueing a ray, and keeps waves
 // fat (a deep queue is only drained early when it is full).
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -17,6 +18,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -98,6 +100,9 @@ struct RtxScene {
     DevBuf<uchar4> o_rgba; DevBuf<float> o_normals, o_depth; DevBuf<uint32_t> o_ids;
     // probe staging
     DevBuf<ProbeRay> p_rays; DevBuf<ProbeHit> p_hits;
+    // async frame (RendererManager::start / stop / is_done)
+    std::thread worker; std::atomic<bool> running{false}, cancel{false}; std::atomic<uint64_t> samples_issued{0};
+    uint64_t async_pixels = 0; uint32_t async_samples = 1; int async_result = RTX_OK; RtxStats async_stats{}; std::string async_err;
 };
 
 namespace {
@@ -475,6 +480,8 @@ int rtx_scene_create(const RtxSceneDesc* d, int device, RtxScene** out) {
 
 int rtx_scene_destroy(RtxScene* sc) {
     if (!sc) return RTX_OK;
+    sc->cancel.store(true);
+    if (sc->worker.joinable()) sc->worker.join();
     cudaSetDevice(sc->device);
     cudaDeviceSynchronize();
     sc->nodes.release(); sc->tris.release(); sc->items.release(); sc->tlas_prims.release();
@@ -610,6 +617,7 @@ int rtx_render_frame_device(RtxScene* sc, const RtxCamera* cam, const RtxConfig*
     ShadowQ SQ{sc->s_o.p, sc->s_d.p, sc->s_c.p, sc->s_r.p};
 
     for (;;) {
+        if (sc->cancel.load(std::memory_order_relaxed)) { CU(cudaStreamSynchronize(st)); return fail(RTX_E_CANCELLED, "frame cancelled by rtx_render_stop"); }
         int level = -1;
         for (int d = (int)L; d >= 1; d--) if (counts[d] >= chunk) { level = d; break; }
         if (level < 0 && primary_left) level = 0;
@@ -621,6 +629,7 @@ int rtx_render_frame_device(RtxScene* sc, const RtxCamera* cam, const RtxConfig*
             raygen_kernel<<<std::min<uint32_t>((n + 255) / 256, gs), 256, 0, st>>>(F, pl->d.p, cur_p0, np, cur_s0, ns, level_queue(*sc, 1), counts[1]);
             launches++; batches++;
             counts[1] += n; primary += n;
+            sc->samples_issued.store(primary, std::memory_order_relaxed);
             cur_s0 += ns;
             if (cur_s0 >= cfg->samples) { cur_s0 = 0; cur_p0 += np; if (cur_p0 >= pl->n) primary_left = false; }
             continue;
@@ -749,6 +758,48 @@ int rtx_render_frame(RtxScene* sc, const RtxCamera* cam, const RtxConfig* cfg, u
     if (depth) { CU(cudaMemcpy(depth, sc->o_depth.p, n * 4, cudaMemcpyDeviceToHost)); st.d2h_bytes += n * 4; }
     if (object_ids) { CU(cudaMemcpy(object_ids, sc->o_ids.p, n * 4, cudaMemcpyDeviceToHost)); st.d2h_bytes += n * 4; }
     if (stats) *stats = st;
+    return RTX_OK;
+}
+
+// ---- non-blocking frame (reference src/renderer.rs:105-231) ---------------------------------------------
+int rtx_render_frame_async(RtxScene* sc, const RtxCamera* cam, const RtxConfig* cfg, uint8_t* rgba, float* normals, float* depth, uint32_t* object_ids) {
+    if (!sc || !cam || !cfg) return fail(RTX_E_INVALID, "null argument");
+    if (sc->running.load()) return fail(RTX_E_BUSY, "a frame is already in flight on this handle");
+    if (sc->worker.joinable()) sc->worker.join();
+    sc->cancel.store(false); sc->samples_issued.store(0);
+    sc->async_pixels = (uint64_t)cam->width * cam->height; sc->async_samples = std::max(1u, cfg->samples);
+    sc->async_result = RTX_OK; sc->running.store(true);
+    const RtxCamera c = *cam; const RtxConfig g = *cfg;
+    sc->worker = std::thread([=]() {
+        int rc = rtx_render_frame(sc, &c, &g, rgba, normals, depth, object_ids, &sc->async_stats);
+        sc->async_result = rc;
+        if (rc) sc->async_err = g_err;                                    // g_err is thread-local: keep the worker's message
+        sc->running.store(false, std::memory_order_release);
+    });
+    return RTX_OK;
+}
+
+int rtx_render_poll(RtxScene* sc, uint64_t* pixels_rendered, int* running, int* done, int* result, RtxStats* stats) {
+    if (!sc) return fail(RTX_E_INVALID, "null argument");
+    const bool run = sc->running.load(std::memory_order_acquire);
+    const bool finished = !run && sc->async_pixels > 0 && sc->async_result == RTX_OK && sc->worker.joinable();
+    uint64_t px = std::min<uint64_t>(sc->samples_issued.load() / sc->async_samples, sc->async_pixels);
+    if (run && px == sc->async_pixels) px = sc->async_pixels - 1;         // is_done() must only turn true when the buffers are filled
+    if (finished) px = sc->async_pixels;
+    if (pixels_rendered) *pixels_rendered = px;
+    if (running) *running = run ? 1 : 0;
+    if (done) *done = finished ? 1 : 0;
+    if (result) *result = run ? RTX_OK : sc->async_result;
+    if (!run && sc->async_result != RTX_OK) g_err = sc->async_err;
+    if (stats && !run) *stats = sc->async_stats;
+    return RTX_OK;
+}
+
+int rtx_render_stop(RtxScene* sc) {
+    if (!sc) return fail(RTX_E_INVALID, "null argument");
+    sc->cancel.store(true);
+    if (sc->worker.joinable()) sc->worker.join();
+    sc->cancel.store(false);
     return RTX_OK;
 }
 

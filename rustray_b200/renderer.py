@@ -149,16 +149,39 @@ class RendererManager(AbiRenderer):
 
     # RendererManager::start (src/renderer.rs:105-172) — blocking on the GPU
     def start(self, cam: abi.RtxCamera, cfg: abi.RtxConfig) -> Frame:
-        self._done = False
+        self._done, self._async = False, False
         self.render(cam, cfg, self.frame)
         self._done = True
         return self.frame
 
-    def is_done(self) -> bool:               # src/renderer.rs:228
+    # Non-blocking path of the GUI: start_async / is_running / is_done / get_rendered_pixels / stop (src/renderer.rs:105-231)
+    def start_async(self, cam: abi.RtxCamera, cfg: abi.RtxConfig) -> None:
+        self._done, self._async = False, True
+        f = self.frame
+        self._keep = (cam, cfg)
+        self._check(self._lib.rtx_render_frame_async(self._h, C.byref(cam), C.byref(cfg), f.image.ctypes.data, f.normals.ctypes.data,
+                                                     f.depth.ctypes.data, f.objects.ctypes.data))
+
+    def _poll(self):
+        px, run, done, res = C.c_uint64(), C.c_int(), C.c_int(), C.c_int()
+        self._check(self._lib.rtx_render_poll(self._h, C.byref(px), C.byref(run), C.byref(done), C.byref(res), C.byref(self.frame.stats)))
+        return int(px.value), bool(run.value), bool(done.value), int(res.value)
+
+    def is_running(self) -> bool:            # src/renderer.rs:221-227
+        return self._poll()[1] if getattr(self, "_async", False) else False
+
+    def is_done(self) -> bool:               # src/renderer.rs:228-231
+        if getattr(self, "_async", False):
+            self._done = self._poll()[2]
         return self._done
 
-    def get_rendered_pixels(self) -> int:    # src/renderer.rs:215-221
+    def get_rendered_pixels(self) -> int:    # src/renderer.rs:215-219
+        if getattr(self, "_async", False):
+            return self._poll()[0]
         return self.width * self.height if self._done else 0
+
+    def stop(self) -> None:                  # src/renderer.rs:174-199
+        self._check(self._lib.rtx_render_stop(self._h))
 
     def pick(self, cam: abi.RtxCamera, x: int, y: int):
         """Raytracing::pick (src/raytracing.rs:237-273): (item id, name, distance) or None."""

@@ -290,6 +290,38 @@ def test_degenerate_inputs():
         assert np.array_equal(fg.objects, fc.objects) and np.array_equal(fg.depth, fc.depth) and lsb_stats(fg.image, fc.image)[0] >= 0.999
 
 
+def test_async_frame_progress_and_stop():
+    """'next' row 4: the GUI's non-blocking use of RendererManager (start, is_running, get_rendered_pixels, is_done, stop —
+    reference src/renderer.rs:105-231)."""
+    import time
+    fs, cam, cfg = abi.load_fixture("room_spheres", samples=16, monte_carlo=1, mc_seed=3)
+    cam = abi.resize_camera(cam, 640, 360)
+    g = RendererManager(640, 360, fs)
+    want = g.start(cam, cfg).image.copy()
+    g.frame.image[:] = 0
+    g.start_async(cam, cfg)
+    seen = []
+    while not g.is_done():
+        assert g.is_running() or g.is_done()
+        seen.append(g.get_rendered_pixels())
+        assert seen[-1] < 640 * 360 or g.is_done()
+        time.sleep(0.002)
+    assert g.get_rendered_pixels() == 640 * 360 and not g.is_running()
+    assert seen == sorted(seen)
+    assert lsb_stats(g.frame.image, want)[0] >= 0.9999 and g.frame.stats.rays_closest > 0
+    with pytest.raises(RtxError, match="in flight"):
+        g.start_async(cam, cfg); g.start_async(cam, cfg)
+    g.stop()
+    # stop() in the middle of a long frame: the worker ends with RTX_E_CANCELLED, the handle stays usable
+    big = clone_cfg(cfg, samples=512)
+    g.start_async(cam, big)
+    time.sleep(0.05)
+    g.stop()
+    px, running, done, res = g._poll()
+    assert not running and not done and res == -6 and px < 640 * 360
+    assert lsb_stats(g.start(cam, cfg).image, want)[0] >= 0.9999
+
+
 def test_error_codes_instead_of_panics():
     fs, cam, cfg = abi.load_fixture("c1_spheres")
     g = RendererManager(16, 16, fs)
