@@ -716,6 +716,9 @@ int rtx_render_frame_device(RtxScene* sc, const RtxCamera* cam, const RtxConfig*
     CU(cudaEventRecord(get_event(1), st));
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
+    uint32_t ovf[4]; CU(cudaMemcpy(ovf, sc->overflow.p, 16, cudaMemcpyDeviceToHost));
+    if (ovf[0]) return fail(RTX_E_INVALID, "internal: ray queue overflow");
+    if (ovf[1]) return fail(RTX_E_INVALID, "internal: traversal stack overflow");
     if (stats) {
         memset(stats, 0, sizeof(*stats));
         float ms = 0.f; cudaEventElapsedTime(&ms, sc->events[0], sc->events[1]);
@@ -729,10 +732,7 @@ int rtx_render_frame_device(RtxScene* sc, const RtxCamera* cam, const RtxConfig*
         stats->rays_closest = rays_closest; stats->rays_shadow = rays_shadow; stats->primary_samples = primary;
         stats->kernel_launches = launches; stats->waves = waves; stats->batches = batches;
         stats->h2d_bytes = h2d; stats->d2h_bytes = (uint64_t)waves * 16;
-        {
-            uint32_t ovf[4]; CU(cudaMemcpy(ovf, sc->overflow.p, 16, cudaMemcpyDeviceToHost));
-            stats->rays_shadow_skipped = ovf[2]; stats->rays_shadow += ovf[2];
-        }
+        stats->rays_shadow_skipped = ovf[2]; stats->rays_shadow += ovf[2];
         if (want_stats) {
             Counters c; CU(cudaMemcpy(&c, sc->counters.p, sizeof(c), cudaMemcpyDeviceToHost));
             stats->node_visits[0] = c.node_visits[0]; stats->node_visits[1] = c.node_visits[1];

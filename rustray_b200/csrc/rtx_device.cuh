@@ -620,6 +620,13 @@ __device__ __forceinline__ void lane_init(Lane& L, const SceneDev& S, float3 o, 
     L.cur_item = 0; L.cur_key = 0.0f; L.bkey = 0.0f; L.bitem = 0xFFFFFFFFu; L.bprim = 0; L.bface = 0xFFFFFFFFu; L.bflags = 0;
 }
 
+// Traversal stack exhausted (cannot happen for BVH depths accepted by rtx_scene_create): end this ray and raise the
+// device-side error counter; the frame then returns an error instead of corrupting memory or spinning.
+__device__ __forceinline__ void lane_abort(Lane& L, const SceneDev& S) {
+    atomicAdd(S.dbg, 1u);
+    L.ng = make_uint2(0u, 0u); L.tg = make_uint2(0u, 0u); L.sp = 0; L.blas_base = -1;
+}
+
 // closest-hit merge with the reference's order rule (strictly smaller toi wins; equal toi: earlier in the
 // stable bbox-key sort, i.e. smaller (key, item index); inside one mesh: lowest face index)
 __device__ __forceinline__ void lane_accept(Lane& L, float toi, float key, uint32_t item, uint32_t prim, uint32_t face, uint32_t flags) {
@@ -635,8 +642,8 @@ __device__ __forceinline__ void lane_accept(Lane& L, float toi, float key, uint3
 // later node test produces more — until enough lanes of the warp have some, so triangle tests run on mostly
 // full warps instead of the 4-5 lanes that happen to reach a leaf in the same step.
 template <int MODE, bool STATS>
-__device__ __forceinline__ void lane_node(Lane& L, uint2* __restrict__ stack, const SceneDev& S, TravStats& st) {
-    if (L.sp + 2 > kLaneStack) { atomicAdd(S.dbg, 1u); return; }
+__device__ __forceinline__ void lane_node(Lane& L, uint2* stack, const SceneDev& S, TravStats& st) {
+    if (L.sp + 2 > kLaneStack) { lane_abort(L, S); return; }
     if (L.tg.y != 0u) stack[L.sp++] = L.tg;                               // park postponed leaf entries
     const uint32_t hits = L.ng.y, imask = L.ng.y;
     const uint32_t cbit = bfind(hits);
@@ -665,7 +672,7 @@ __device__ __forceinline__ void lane_any_hit(Lane& L, float key, uint32_t item) 
 }
 
 template <int MODE, bool STATS>
-__device__ __forceinline__ void lane_leaf(Lane& L, uint2* __restrict__ stack, const SceneDev& S, bool for_shadow, uint32_t depth,
+__device__ __forceinline__ void lane_leaf(Lane& L, uint2* stack, const SceneDev& S, bool for_shadow, uint32_t depth,
                                           TravStats& st, uint32_t& n_items, uint32_t& n_sph) {
     const uint32_t ti = bfind(L.tg.y);
     L.tg.y &= ~(1u << ti);
@@ -721,7 +728,7 @@ __device__ __forceinline__ void lane_leaf(Lane& L, uint2* __restrict__ stack, co
     }
     if (MODE == UT_ANY) lane_note_other(L, key, ii);                      // harmless if it becomes the occluder: (key, item) is then not < itself
     // enter the instance: park what is left of the TLAS groups under the BLAS part of the stack
-    if (L.sp + 2 > kLaneStack) { atomicAdd(S.dbg, 1u); return; }
+    if (L.sp + 2 > kLaneStack) { lane_abort(L, S); return; }
     if (L.ng.y > 0x00FFFFFFu) stack[L.sp++] = L.ng;
     if (L.tg.y != 0u) stack[L.sp++] = L.tg;
     L.blas_base = L.sp; L.cur_item = ii; L.cur_key = key;
@@ -730,7 +737,7 @@ __device__ __forceinline__ void lane_leaf(Lane& L, uint2* __restrict__ stack, co
 }
 
 // Both groups empty: leave the instance if its part of the stack is drained, then pop.  Returns true when the ray is done.
-__device__ __forceinline__ bool lane_pop(Lane& L, const uint2* __restrict__ stack) {
+__device__ __forceinline__ bool lane_pop(Lane& L, const uint2* stack) {
     if (L.blas_base >= 0 && L.sp == L.blas_base) { L.blas_base = -1; L.r = L.w; }
     if (L.sp == 0) return true;
     const uint2 e = stack[--L.sp];
