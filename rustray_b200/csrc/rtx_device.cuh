@@ -643,7 +643,9 @@ __device__ __forceinline__ void lane_accept(Lane& L, float toi, float key, uint3
 // full warps instead of the 4-5 lanes that happen to reach a leaf in the same step.
 template <int MODE, bool STATS>
 __device__ __forceinline__ void lane_node(Lane& L, uint2* stack, const SceneDev& S, TravStats& st) {
+#ifndef RTX_NO_GUARD
     if (L.sp + 2 > kLaneStack) { lane_abort(L, S); return; }
+#endif
     if (L.tg.y != 0u) stack[L.sp++] = L.tg;                               // park postponed leaf entries
     const uint32_t hits = L.ng.y, imask = L.ng.y;
     const uint32_t cbit = bfind(hits);
@@ -728,7 +730,9 @@ __device__ __forceinline__ void lane_leaf(Lane& L, uint2* stack, const SceneDev&
     }
     if (MODE == UT_ANY) lane_note_other(L, key, ii);                      // harmless if it becomes the occluder: (key, item) is then not < itself
     // enter the instance: park what is left of the TLAS groups under the BLAS part of the stack
+#ifndef RTX_NO_GUARD
     if (L.sp + 2 > kLaneStack) { lane_abort(L, S); return; }
+#endif
     if (L.ng.y > 0x00FFFFFFu) stack[L.sp++] = L.ng;
     if (L.tg.y != 0u) stack[L.sp++] = L.tg;
     L.blas_base = L.sp; L.cur_item = ii; L.cur_key = key;

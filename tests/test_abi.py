@@ -104,3 +104,11 @@ def test_product_never_imports_the_oracle():
                 assert "liboracle" not in code and "from oracle" not in code and "import oracle" not in code and "rt_oracle" not in code, f
     out = subprocess.check_output(["ldd", renderer.lib_path()]).decode()
     assert "oracle" not in out
+
+
+def test_traversal_kernel_votes_are_protected_in_the_built_sass():
+    """The persistent kernels' warp votes must be compiled with the BRA.DIV / WARPSYNC slow path (a build with bare VOTEs
+    lost ray indices on B200 — DESIGN.md 'A codegen trap'); __graft_entry__.build() enforces it, this test re-checks the
+    library that is actually shipped."""
+    import __graft_entry__ as g
+    g.check_vote_convergence(renderer.lib_path())
