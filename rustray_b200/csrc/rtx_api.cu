@@ -76,7 +76,7 @@ struct RtxScene {
     int device = 0; int sm_count = 148;
     // host mirrors needed for updates
     std::vector<RtxItem> src_items; std::vector<DItem> h_items; std::vector<RtxMaterial> src_mats;
-    std::vector<uint32_t> mesh_root; std::vector<RtxMesh> mesh_meta;
+    std::vector<uint32_t> mesh_root, mesh_tri_base; std::vector<RtxMesh> mesh_meta;
     uint32_t n_blas_nodes = 0, n_tris = 0, tlas_cap = 0, n_tlas_nodes = 0;
     size_t texture_bytes = 0; float build_ms = 0.f;
     // device scene
@@ -365,7 +365,7 @@ int rtx_scene_create(const RtxSceneDesc* d, int device, RtxScene** out) {
     std::vector<float> h_verts, h_uvs, h_nrms; std::vector<uint32_t> h_idx, h_uvidx, h_nidx;
     struct MeshOff { uint32_t vert, idx, uv, uvidx, nrm, nidx; float lo[3], hi[3]; };
     std::vector<MeshOff> moff(d->n_meshes);
-    sc->mesh_root.resize(d->n_meshes);
+    sc->mesh_root.resize(d->n_meshes); sc->mesh_tri_base.resize(d->n_meshes);
     sc->mesh_meta.assign(d->meshes, d->meshes + d->n_meshes);
     for (uint32_t mi = 0; mi < d->n_meshes; mi++) {
         const RtxMesh& m = d->meshes[mi];
@@ -397,7 +397,7 @@ int rtx_scene_create(const RtxSceneDesc* d, int device, RtxScene** out) {
         WideBvh bvh; build_wide_bvh(boxes.data(), m.n_faces, bvh);
         if (bvh.max_depth >= kStack - 2 || 2 * bvh.max_depth + 2 * 6 + 4 > kLaneStack) return bail(RTX_E_INVALID, "BLAS too deep for the traversal stack");
         const uint32_t node_off = (uint32_t)(h_nodes.size() / 5), tri_off = (uint32_t)(h_tris.size() / 3);
-        sc->mesh_root[mi] = node_off;
+        sc->mesh_root[mi] = node_off; sc->mesh_tri_base[mi] = tri_off;
         append_nodes(h_nodes, bvh, node_off, tri_off);
         for (uint32_t f : bvh.prim_order) {
             const float* a = m.vertices + 3 * (size_t)m.indices[3 * (size_t)f];
@@ -419,7 +419,8 @@ int rtx_scene_create(const RtxSceneDesc* d, int device, RtxScene** out) {
         if (s.shape == RTX_SHAPE_MESH) {
             const RtxMesh& m = d->meshes[s.mesh]; const MeshOff& o = moff[s.mesh];
             di.lo = make_float4(o.lo[0], o.lo[1], o.lo[2], 0.f); di.hi.x = o.hi[0]; di.hi.y = o.hi[1]; di.hi.z = o.hi[2];
-            di.root = sc->mesh_root[s.mesh];
+            di.root = sc->mesh_root[s.mesh]; di.tri_base = sc->mesh_tri_base[s.mesh];
+            if (m.n_faces <= kDirectTris && !getenv("RTX_NO_DIRECT_TRIS")) di.flags |= IF_DIRECT_TRIS;
             di.n_faces = m.n_faces; di.n_uv_faces = m.n_uv_faces; di.n_normal_faces = m.n_normal_faces;
             di.vert_off = o.vert; di.idx_off = o.idx; di.uv_off = o.uv; di.uvidx_off = o.uvidx; di.nrm_off = o.nrm; di.nidx_off = o.nidx;
             if (m.n_normals > 0 && m.n_normal_faces > 0) di.flags |= IF_HAS_NORMALS;

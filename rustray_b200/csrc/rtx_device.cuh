@@ -32,8 +32,10 @@ enum : uint32_t {
     IF_MESH = 1u, IF_VISIBLE = 2u, IF_FLIP = 4u, IF_CAST_SHADOW = 8u, IF_REFL_ONLY = 16u, IF_BACKFACE = 32u,
     IF_SMOOTH = 64u, IF_HAS_NORMALS = 128u, IF_ALPHA_TEX = 256u, IF_ALPHA_POS = 512u, IF_ALPHA_LT1 = 1024u,
     IF_DIV_W = 4096u,          // tran_inverse[3][3] != 1 (rounding of the cofactor inverse): points are divided by it, like from_homogeneous
-    IF_TRANSLATION = 2048u     // tran_inverse is identity + translation: o' = o + t, d' = d (bit-identical to the general product)
+    IF_TRANSLATION = 2048u,    // tran_inverse is identity + translation: o' = o + t, d' = d (bit-identical to the general product)
+    IF_DIRECT_TRIS = 8192u     // mesh of <= kDirectTris triangles (quads, planes): entering the item queues its triangles, no BLAS node visit
 };
+constexpr uint32_t kDirectTris = 4;
 
 struct alignas(16) DItem {
     float4 inv[3];      // rows 0..2 of tran_inverse (affine)
@@ -43,7 +45,7 @@ struct alignas(16) DItem {
     uint32_t flags, id, material, root;               // root = BLAS root node (mesh)
     uint32_t n_faces, n_uv_faces, n_normal_faces; float inv_w;   // inv_w = tran_inverse[3][3]: Point3::from_homogeneous divides by it
     uint32_t vert_off, idx_off, uv_off, uvidx_off;    // element offsets into the mesh arrays
-    uint32_t nrm_off, nidx_off, pad1, pad2;
+    uint32_t nrm_off, nidx_off, tri_base, pad2;          // tri_base = first triangle of the mesh in `tris`
     float4 wlo, whi;    // padded world-space AABB (the TLAS leaf box): cheap pre-cull when the item list is walked without a TLAS
 };
 
@@ -737,7 +739,8 @@ __device__ __forceinline__ void lane_leaf(Lane& L, uint2* stack, const SceneDev&
     if (L.tg.y != 0u) stack[L.sp++] = L.tg;
     L.blas_base = L.sp; L.cur_item = ii; L.cur_key = key;
     L.r = make_wide_ray(lo3, ld3);
-    L.ng = make_uint2(it->root, 0x80000000u); L.tg = make_uint2(0u, 0u);
+    if (flags & IF_DIRECT_TRIS) { L.ng = make_uint2(0u, 0u); L.tg = make_uint2(it->tri_base, (1u << it->n_faces) - 1u); }
+    else { L.ng = make_uint2(it->root, 0x80000000u); L.tg = make_uint2(0u, 0u); }
 }
 
 // Both groups empty: leave the instance if its part of the stack is drained, then pop.  Returns true when the ray is done.
