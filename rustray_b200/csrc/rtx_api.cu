@@ -456,6 +456,8 @@ int rtx_scene_create(const RtxSceneDesc* d, int device, RtxScene** out) {
         o.alpha = m.alpha; o.shininess = m.shininess; o.reflectivity = m.reflectivity; o.refraction_index = m.refraction_index;
         o.normal_map_strength = m.normal_map_strength; o.shadow_softness = m.shadow_softness; o.roughness = m.roughness;
         o.nearest = m.texture_filtering_nearest; o.receive_shadow = m.receive_shadow; o.monte_carlo = m.monte_carlo;
+        o.shadow_z_lo = m.shadow_softness <= 0.0f ? 1.0f : cosf(m.shadow_softness * 3.14159265358979323846f);   // jitter(): z range
+        o.rough_z_lo = m.roughness <= 0.0f ? 1.0f : cosf(m.roughness * 3.14159265358979323846f);
         for (int t = 0; t < 8; t++) {
             o.tex[t] = (m.texture[t] >= 0 && d->textures[m.texture[t]].width > 0) ? m.texture[t] : -1;
             if (o.tex[t] >= 0) o.any_texture = 1;

@@ -56,6 +56,7 @@ struct alignas(16) DMaterial {
     float refraction_index, normal_map_strength, shadow_softness, roughness;
     int32_t tex[8];
     uint32_t nearest, receive_shadow, monte_carlo, any_texture;
+    float shadow_z_lo, rough_z_lo; uint32_t pad[2];     // cos(spread * pi) of jitter() for the two per-material spreads (host libm, like the oracle)
 };
 
 struct DTex { uint32_t offset_lo, offset_hi, w, h; };     // texel offset (64-bit) into the pool
@@ -135,6 +136,7 @@ __device__ __forceinline__ float dot3(float3 a, float3 b) { return a.x * b.x + a
 __device__ __forceinline__ float3 cross3(float3 a, float3 b) { return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 __device__ __forceinline__ float len3(float3 a) { return sqrtf(dot3(a, a)); }
 __device__ __forceinline__ float3 norm3(float3 a) { float n = len3(a); return f3(a.x / n, a.y / n, a.z / n); }
+__device__ __forceinline__ float3 norm3_fast(float3 a) { const float s = rsqrtf(dot3(a, a)); return f3(a.x * s, a.y * s, a.z * s); }   // MUFU.RSQ: Monte-Carlo directions only
 
 // Rust `as` casts: saturating, NaN -> 0
 __device__ __forceinline__ uint32_t as_u32(float f) { return __float2uint_rz(f); }
@@ -144,12 +146,18 @@ __device__ __forceinline__ bool approx_equal(float a, float b) { return truncf(x
 
 // counter-based RNG — identical to oracle/rt_oracle.cpp mc_uniform
 __device__ __forceinline__ uint32_t mix32(uint32_t h) { h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16; return h; }
-__device__ __forceinline__ float mc_uniform(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t path, uint32_t slot) {
+// split in two so that the (seed, pixel, sample) part is hashed once per ray and each draw costs one round
+__device__ __forceinline__ uint32_t mc_base(uint32_t seed, uint32_t pixel, uint32_t sample) {
     uint32_t h = mix32(seed ^ 0x9E3779B9u);
     h = mix32(h ^ (pixel * 0x85EBCA6Bu + 0x165667B1u));
-    h = mix32(h ^ (sample * 0xC2B2AE35u + 0x27D4EB2Fu));
-    h = mix32(h ^ (path * 0x9E3779B1u + slot * 0x632BE5ABu + 0x7F4A7C15u));
+    return mix32(h ^ (sample * 0xC2B2AE35u + 0x27D4EB2Fu));
+}
+__device__ __forceinline__ float mc_draw(uint32_t base, uint32_t path, uint32_t slot) {
+    const uint32_t h = mix32(base ^ (path * 0x9E3779B1u + slot * 0x632BE5ABu + 0x7F4A7C15u));
     return __fmul_rn((float)(h >> 8), 1.0f / 16777216.0f);
+}
+__device__ __forceinline__ float mc_uniform(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t path, uint32_t slot) {
+    return mc_draw(mc_base(seed, pixel, sample), path, slot);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -891,21 +899,23 @@ __device__ __forceinline__ float fresnel(float3 incident, float3 normal, float i
     const float r_p = ((eta_i * cos_i) - (eta_t * cos_t)) / ((eta_i * cos_i) + (eta_t * cos_t));
     return (r_s * r_s + r_p * r_p) / 2.0f;
 }
-__device__ RTX_SHADE_INLINE float3 jitter(float3 dir, float spread, uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t path, uint32_t slot) {
+// jitter (reference src/raytracing.rs:565-626).  z_lo = cos(spread * pi).  The sampled direction is Monte-Carlo data
+// (the reference draws from thread_rng), so the basis and the trigonometry use the fast units; the uniforms are the
+// oracle's bit for bit.
+__device__ RTX_SHADE_INLINE float3 jitter(float3 dir, float z_lo, uint32_t rng, uint32_t path, uint32_t slot) {
     const float PI = 3.14159265358979323846f;
-    if (spread <= 0.0f) return dir;
-    const float3 b3 = norm3(dir);
+    if (!(z_lo < 1.0f)) return dir;                                  // spread <= 0 (host stores 1) or empty z range
+    const float3 b3 = norm3_fast(dir);
     const float3 diff = fabsf(b3.x) < 0.5f ? f3(1, 0, 0) : f3(0, 1, 0);
-    const float3 b1 = norm3(cross3(b3, diff));
+    const float3 b1 = norm3_fast(cross3(b3, diff));
     const float3 b2 = cross3(b1, b3);
-    const float z_lo = cosf(spread * PI);
-    if (!(z_lo < 1.0f)) return dir;
-    const float z = z_lo + mc_uniform(seed, pixel, sample, path, slot) * (1.0f - z_lo);
+    const float z = z_lo + mc_draw(rng, path, slot) * (1.0f - z_lo);
     const float r = sqrtf(1.0f - z * z);
-    const float theta = -PI + mc_uniform(seed, pixel, sample, path, slot + 1) * (PI - (-PI));
-    float sn, cs; sincosf(theta, &sn, &cs);
-    return norm3((r * cs) * b1 + (r * sn) * b2 + z * b3);
+    const float theta = -PI + mc_draw(rng, path, slot + 1) * (PI - (-PI));
+    float sn, cs; __sincosf(theta, &sn, &cs);
+    return norm3_fast((r * cs) * b1 + (r * sn) * b2 + z * b3);
 }
+__device__ __forceinline__ float jitter_z_lo(float spread) { return spread <= 0.0f ? 1.0f : cosf(spread * 3.14159265358979323846f); }
 
 // warp-aggregated queue append: returns the slot of this lane (valid only where `emit`)
 __device__ __forceinline__ uint32_t queue_append(uint32_t* counter, bool emit) {

@@ -315,12 +315,15 @@ __global__ void __launch_bounds__(kShadeBlock, RTX_SHADE_MIN_BLOCKS) shade_kerne
         // per-light shadow payloads are produced inside the light loop (warp-aggregated per light)
         float3 hit_point = f3(0, 0, 0), surface_normal = f3(0, 0, 1); float coef_d = 0.0f;
         float4 base_color = make_float4(0, 0, 0, 0), specular_color = make_float4(0, 0, 0, 0);
-        float shininess = 0.0f, mat_alpha = 1.0f, shadow_softness = 0.0f; bool recv_shadow = false, mat_mc = false;
+        float shininess = 0.0f, mat_alpha = 1.0f, shadow_z_lo = 1.0f; bool recv_shadow = false, mat_mc = false;
         float3 direct = f3(0, 0, 0), constant = f3(0, 0, 0);
 
+        const uint32_t rng = F.monte_carlo ? mc_base(F.mc_seed, pixel, sample) : 0u;
+        float3 view_dir = f3(0, 0, 1);
         if (hit) {
             const DItem& item = S.items[h.item];
             const DMaterial& mat = S.mats[item.material];
+            view_dir = norm3(-d);
             uint32_t face_id;
             const float3 normal = hit_normal(S, item, o, d, h.t, h.prim, h.flags, face_id);
             const float hit_dist = h.t;
@@ -360,7 +363,7 @@ __global__ void __launch_bounds__(kShadeBlock, RTX_SHADE_MIN_BLOCKS) shade_kerne
             if (F.monte_carlo && mat.monte_carlo && (mat.roughness > 0.0f || has_rough)) {
                 float roughness = mat.roughness;
                 if (has_rough) roughness = (1.0f / PI / 2.0f) * tc.x;
-                surface_normal = jitter(surface_normal, roughness, F.mc_seed, pixel, sample, path, 0);
+                surface_normal = jitter(surface_normal, has_rough ? jitter_z_lo(roughness) : mat.rough_z_lo, rng, path, 0);
             }
             float4 ambient_color = make_float4(mat.ambient[0], mat.ambient[1], mat.ambient[2], 1.0f);   // :801-803
             if ((tex_mask >> 1) & 1u) { tc = texc[1]; ambient_color.x *= tc.x; ambient_color.y *= tc.y; ambient_color.z *= tc.z; }
@@ -396,7 +399,7 @@ __global__ void __launch_bounds__(kShadeBlock, RTX_SHADE_MIN_BLOCKS) shade_kerne
                 emit_trans = true; w_trans = thru * kt;
                 if ((rflags & RF_ID_OWNER) && approx_equal(alpha, 0.0f)) trans_flags = RF_ID_OWNER;   // :966-969
             }
-            shininess = mat.shininess; mat_alpha = mat.alpha; shadow_softness = mat.shadow_softness;
+            shininess = mat.shininess; mat_alpha = mat.alpha; shadow_z_lo = mat.shadow_z_lo;
             recv_shadow = mat.receive_shadow != 0; mat_mc = mat.monte_carlo != 0;
         }
 
@@ -411,7 +414,6 @@ __global__ void __launch_bounds__(kShadeBlock, RTX_SHADE_MIN_BLOCKS) shade_kerne
                 const float dot_light = fmaxf(dot3(surface_normal, dtl), 0.0f);
                 const float3 mi = -dtl;
                 const float3 reflect_dir = mi - (2.0f * dot3(surface_normal, mi)) * surface_normal;
-                const float3 view_dir = norm3(-d);
                 const float spec_dot = fmaxf(dot3(reflect_dir, view_dir), 0.0f);
                 const float light_power = powf(spec_dot, shininess);
                 float intensity;
@@ -434,7 +436,7 @@ __global__ void __launch_bounds__(kShadeBlock, RTX_SHADE_MIN_BLOCKS) shade_kerne
                 else if (recv_shadow) {
                     emit = true;
                     sdir = dtl;
-                    if (F.monte_carlo && mat_mc) sdir = jitter(sdir, shadow_softness, F.mc_seed, pixel, sample, path, 2 + 2 * li);
+                    if (F.monte_carlo && mat_mc) sdir = jitter(sdir, shadow_z_lo, rng, path, 2 + 2 * li);
                 } else direct = direct + c;
             }
             const uint32_t slot = queue_append(out.shadow_count, emit);
