@@ -383,18 +383,36 @@ int rtx_scene_create(const RtxSceneDesc* d, int device, RtxScene** out) {
         if (m.n_uv_faces) h_uvidx.insert(h_uvidx.end(), m.uv_indices, m.uv_indices + 3 * (size_t)m.n_uv_faces);
         if (m.n_normals) h_nrms.insert(h_nrms.end(), m.normals, m.normals + 3 * (size_t)m.n_normals);
         if (m.n_normal_faces) h_nidx.insert(h_nidx.end(), m.normals_indices, m.normals_indices + 3 * (size_t)m.n_normal_faces);
-        std::vector<Aabb3> boxes(m.n_faces);
-        for (int k = 0; k < 3; k++) { o.lo[k] = INFINITY; o.hi[k] = -INFINITY; }
-        for (uint32_t f = 0; f < m.n_faces; f++) {
-            Aabb3& b = boxes[f];
-            for (int k = 0; k < 3; k++) { b.lo[k] = INFINITY; b.hi[k] = -INFINITY; }
-            for (int c = 0; c < 3; c++) {
-                const float* v = m.vertices + 3 * (size_t)m.indices[3 * (size_t)f + c];
-                for (int k = 0; k < 3; k++) { b.lo[k] = std::min(b.lo[k], v[k]); b.hi[k] = std::max(b.hi[k], v[k]); }
+    }
+    // BLAS builds are independent: one host thread per mesh, up to the hardware concurrency (config 5: 64 meshes of 156 k triangles)
+    std::vector<WideBvh> bvhs(d->n_meshes);
+    {
+        std::atomic<uint32_t> next{0};
+        auto work = [&]() {
+            for (uint32_t mi = next.fetch_add(1); mi < d->n_meshes; mi = next.fetch_add(1)) {
+                const RtxMesh& m = d->meshes[mi]; MeshOff& o = moff[mi];
+                std::vector<Aabb3> boxes(m.n_faces);
+                for (int k = 0; k < 3; k++) { o.lo[k] = INFINITY; o.hi[k] = -INFINITY; }
+                for (uint32_t f = 0; f < m.n_faces; f++) {
+                    Aabb3& b = boxes[f];
+                    for (int k = 0; k < 3; k++) { b.lo[k] = INFINITY; b.hi[k] = -INFINITY; }
+                    for (int c = 0; c < 3; c++) {
+                        const float* v = m.vertices + 3 * (size_t)m.indices[3 * (size_t)f + c];
+                        for (int k = 0; k < 3; k++) { b.lo[k] = std::min(b.lo[k], v[k]); b.hi[k] = std::max(b.hi[k], v[k]); }
+                    }
+                    for (int k = 0; k < 3; k++) { o.lo[k] = std::min(o.lo[k], b.lo[k]); o.hi[k] = std::max(o.hi[k], b.hi[k]); }   // TriMesh::aabb
+                }
+                build_wide_bvh(boxes.data(), m.n_faces, bvhs[mi]);
             }
-            for (int k = 0; k < 3; k++) { o.lo[k] = std::min(o.lo[k], b.lo[k]); o.hi[k] = std::max(o.hi[k], b.hi[k]); }   // TriMesh::aabb
-        }
-        WideBvh bvh; build_wide_bvh(boxes.data(), m.n_faces, bvh);
+        };
+        const uint32_t nt = std::min<uint32_t>(d->n_meshes, std::max(1u, std::thread::hardware_concurrency()));
+        std::vector<std::thread> pool;
+        for (uint32_t t = 1; t < nt; t++) pool.emplace_back(work);
+        work();
+        for (std::thread& t : pool) t.join();
+    }
+    for (uint32_t mi = 0; mi < d->n_meshes; mi++) {
+        const RtxMesh& m = d->meshes[mi]; const WideBvh& bvh = bvhs[mi];
         if (bvh.max_depth >= kStack - 2 || 2 * bvh.max_depth + 2 * 6 + 4 > kLaneStack) return bail(RTX_E_INVALID, "BLAS too deep for the traversal stack");
         const uint32_t node_off = (uint32_t)(h_nodes.size() / 5), tri_off = (uint32_t)(h_tris.size() / 3);
         sc->mesh_root[mi] = node_off; sc->mesh_tri_base[mi] = tri_off;
@@ -408,6 +426,7 @@ int rtx_scene_create(const RtxSceneDesc* d, int device, RtxScene** out) {
             h_tris.push_back(make_float4(b[0], b[1], b[2], 0.f));
             h_tris.push_back(make_float4(c[0], c[1], c[2], 0.f));
         }
+        bvhs[mi] = WideBvh();                                             // release as we go
     }
     sc->n_blas_nodes = (uint32_t)(h_nodes.size() / 5); sc->n_tris = (uint32_t)(h_tris.size() / 3);
 

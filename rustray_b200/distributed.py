@@ -120,3 +120,49 @@ class ShardedRenderer:
                     rc = lib.rtx_shard_unpack(self.w, self.h, C.byref(sh), self.recv[r].data_ptr(), self.rgba.data_ptr(),
                                               self.normals.data_ptr(), self.depth.data_ptr(), self.ids.data_ptr(), stream)
                     self.rm._check(rc)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# frame-parallel animation: the frames of a keyframe animation are independent once
+# Scene::apply_frame has produced the item transforms (reference src/scene.rs:1695-1713, src/run.rs:422-485),
+# so rank r renders whole frames r, r+N, r+2N, ... on its own GPU and rank 0 receives them in frame order.
+# ---------------------------------------------------------------------------------------------------------
+def frames_for_rank(n_frames: int, rank: int, world: int) -> List[int]:
+    return list(range(rank, n_frames, world))
+
+
+def render_animation_frame_parallel(render_frame, n_frames: int, width: int, height: int, rank: int, world: int,
+                                    on_frame=None, device=None, group=None) -> List[int]:
+    """`render_frame(f) -> renderer.Frame` renders animation frame f on this rank (apply the frame's transforms with
+    RendererManager.update_items, then start()).  Frames are produced in rounds of `world`; after each round ONE gather
+    brings the round's packed frames (24 B/pixel) to rank 0, which calls `on_frame(f, Frame)` in increasing f — the order
+    Run::save_image numbers its output files in.  Returns the frames this rank rendered."""
+    import torch
+    from .renderer import Frame
+    n = width * height
+    all_px = np.arange(n, dtype=np.uint32)
+    dev = device if device is not None else torch.device("cpu")
+    mine = []
+    for first in range(0, n_frames, world):
+        f = first + rank
+        send = torch.zeros(24 * n, dtype=torch.uint8)
+        if f < n_frames:
+            fr = render_frame(f)
+            mine.append(f)
+            send = torch.from_numpy(pack_numpy(all_px, fr.image, fr.normals, fr.depth, fr.objects))
+        if world == 1:
+            if on_frame is not None:
+                on_frame(f, fr)
+            continue
+        import torch.distributed as dist
+        send = send.to(dev)
+        recv = [torch.zeros(24 * n, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
+        dist.gather(send, recv, dst=0, group=group)
+        if rank == 0 and on_frame is not None:
+            for r in range(world):
+                if first + r >= n_frames:
+                    break
+                out = Frame(width, height)
+                unpack_numpy(all_px, recv[r].cpu().numpy(), out.image, out.normals, out.depth, out.objects)
+                on_frame(first + r, out)
+    return mine
