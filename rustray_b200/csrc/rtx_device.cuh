@@ -115,6 +115,15 @@ __device__ __forceinline__ float3 xcross(float3 a, float3 b) {
 }
 __device__ __forceinline__ float xnorm(float3 a) { return xsqrt(xdot(a, a)); }
 __device__ __forceinline__ float3 xnormalize(float3 a) { float n = xnorm(a); return f3(xd(a.x, n), xd(a.y, n), xd(a.z, n)); }
+// out-of-line copy for the shade kernel (13 call sites of sqrt + 3 IEEE divisions): keeps its code inside the instruction cache
+#ifndef RTX_XNORM_NOINLINE
+#define RTX_XNORM_NOINLINE 1
+#endif
+#if RTX_XNORM_NOINLINE
+__device__ __noinline__ float3 xnormalize_s(float3 a) { float n = xnorm(a); return f3(xd(a.x, n), xd(a.y, n), xd(a.z, n)); }
+#else
+__device__ __forceinline__ float3 xnormalize_s(float3 a) { return xnormalize(a); }
+#endif
 // row r of an affine 3x4 (row = m[r][0..3]) times (x,y,z,w): ((m0*x + m1*y) + m2*z) + m3*w
 __device__ __forceinline__ float xrow(float4 r, float3 v, float w) { return xa(xa(xa(xm(r.x, v.x), xm(r.y, v.y)), xm(r.z, v.z)), xm(r.w, w)); }
 __device__ __forceinline__ float3 xform_point(const float4 m[3], float3 p) { return f3(xrow(m[0], p, 1.0f), xrow(m[1], p, 1.0f), xrow(m[2], p, 1.0f)); }
@@ -236,6 +245,22 @@ __device__ __forceinline__ uint32_t bfind(uint32_t x) { return 31u - __clz(x); }
 #endif
 __device__ __forceinline__ float byte_as_f23(uint32_t x, int j) { return __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7650u + j)); }   // 2^23 + byte j
 
+// Blackwell packed FP32 (SASS FFMA2: two IEEE fused multiply-adds per instruction).  Tried for the six plane distances of a
+// child (3 instructions instead of 6, clean codegen with the scalar operand broadcast): measured 1.5 % SLOWER on config 2,
+// i.e. FFMA2 does not save issue bandwidth on this kernel.  Kept as a compile-time switch, off.
+#ifndef RTX_FFMA2
+#define RTX_FFMA2 0
+#endif
+__device__ __forceinline__ void ffma2(float a0, float a1, float b0, float b1, float c0, float c1, float& r0, float& r1) {
+#if RTX_FFMA2
+    asm("{ .reg .b64 a, b, c, r;\n\t mov.b64 a, {%2, %3};\n\t mov.b64 b, {%4, %5};\n\t mov.b64 c, {%6, %7};\n\t"
+        " fma.rn.f32x2 r, a, b, c;\n\t mov.b64 {%0, %1}, r; }"
+        : "=f"(r0), "=f"(r1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+#else
+    r0 = fmaf(a0, b0, c0); r1 = fmaf(a1, b1, c1);
+#endif
+}
+
 struct TravStats { uint32_t nodes, tris; };
 struct MeshHit { float t; uint32_t prim, face, back; };
 enum { TM_CLOSEST = 0, TM_ANY_LE = 1, TM_ANY_GT = 2, TM_CLASSIFY = 3 };
@@ -295,10 +320,11 @@ __device__ __forceinline__ uint32_t node_test(const float4* __restrict__ nodes, 
         const uint32_t zn = r.d.z < 0.0f ? qhiz : qloz, zf = r.d.z < 0.0f ? qloz : qhiz;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-#if RTX_DEQUANT == 0      // all six planes through I2F.U8 (XU pipe)
-            const float t0x = fmaf((float)byte_of(xn, j), ax, bx - px), t1x = fmaf((float)byte_of(xf, j), ax, bx + px);
-            const float t0y = fmaf((float)byte_of(yn, j), ay, by - py), t1y = fmaf((float)byte_of(yf, j), ay, by + py);
-            const float t0z = fmaf((float)byte_of(zn, j), az, bz - pz), t1z = fmaf((float)byte_of(zf, j), az, bz + pz);
+#if RTX_DEQUANT == 0      // all six planes through I2F.U8 (XU pipe), near/far pairs through one FFMA2 per axis
+            float t0x, t1x, t0y, t1y, t0z, t1z;
+            ffma2((float)byte_of(xn, j), (float)byte_of(xf, j), ax, ax, bx - px, bx + px, t0x, t1x);
+            ffma2((float)byte_of(yn, j), (float)byte_of(yf, j), ay, ay, by - py, by + py, t0y, t1y);
+            ffma2((float)byte_of(zn, j), (float)byte_of(zf, j), az, az, bz - pz, bz + pz, t0z, t1z);
 #elif RTX_DEQUANT == 1    // all six through PRMT (ALU pipe)
             const float t0x = fmaf(byte_as_f23(xn, j), ax, blx), t1x = fmaf(byte_as_f23(xf, j), ax, bhx);
             const float t0y = fmaf(byte_as_f23(yn, j), ay, bly), t1y = fmaf(byte_as_f23(yf, j), ay, bhy);
@@ -801,10 +827,10 @@ __device__ __forceinline__ float3 hit_normal(const SceneDev& S, const DItem& it,
                                              uint32_t& face_id) {
     if (!(it.flags & IF_MESH)) {
         const float3 lo3 = xform_point_w(it.inv, o, it.flags, it.inv_w), ld = xform_vec(it.inv, d);
-        float3 n = xnormalize(xadd(lo3, xscale(ld, t)));
+        float3 n = xnormalize_s(xadd(lo3, xscale(ld, t)));
         if ((hflags & HF_INSIDE) && S.ball_flip_inside) n = xneg(n);
         face_id = 0;
-        return xnormalize(xform_vec(it.mat, n));
+        return xnormalize_s(xform_vec(it.mat, n));
     }
     const float4* tp = S.tris + (size_t)prim * 3;
     const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
@@ -819,13 +845,13 @@ __device__ __forceinline__ float3 hit_normal(const SceneDev& S, const DItem& it,
         const float3 a = ld3(S.nrms + it.nrm_off, __ldg(ni)), b = ld3(S.nrms + it.nrm_off, __ldg(ni + 1)), c = ld3(S.nrms + it.nrm_off, __ldg(ni + 2));
         const float3 p1 = xscale(a, w[0]), p2 = xscale(b, w[1]), p3 = xscale(c, w[2]);
         n = f3(xa(xa(p1.x, p2.x), p3.x), xa(xa(p1.y, p2.y), p3.y), xa(xa(p1.z, p2.z), p3.z));
-        n = xnormalize(xform_vec(it.mat, n));
+        n = xnormalize_s(xform_vec(it.mat, n));
         if (back) n = xneg(n);
     } else {
         const float3 a = f3(v0.x, v0.y, v0.z), b = f3(v1.x, v1.y, v1.z), c = f3(v2.x, v2.y, v2.z);
-        float3 g = xnormalize(xcross(xsub(b, a), xsub(c, a)));
+        float3 g = xnormalize_s(xcross(xsub(b, a), xsub(c, a)));
         if (hflags & HF_NEGN) g = xneg(g);      // parry: normal faces the ray origin
-        n = xnormalize(xform_vec(it.mat, g));
+        n = xnormalize_s(xform_vec(it.mat, g));
     }
     if (it.flags & IF_FLIP) n = xneg(n);
     return n;

@@ -350,12 +350,12 @@ __global__ void __launch_bounds__(kShadeBlock, RTX_SHADE_MIN_BLOCKS) shade_kerne
             if ((tex_mask >> 3) & 1u) { tc = texc[3];                                  // Normal :757-784
                 float3 tangent = xcross(normal, f3(0, 1, 0));
                 if (xnorm(tangent) <= 0.0001f) tangent = xcross(normal, f3(0, 0, 1));
-                tangent = xnormalize(tangent);
-                const float3 bitangent = xnormalize(xcross(normal, tangent));
+                tangent = xnormalize_s(tangent);
+                const float3 bitangent = xnormalize_s(xcross(normal, tangent));
                 float3 nm = f3(xs(xm(tc.x, 2.0f), 1.0f), xs(xm(tc.y, 2.0f), 1.0f), xs(xm(tc.z, 2.0f), 1.0f));
                 nm.x = xm(nm.x, mat.normal_map_strength); nm.y = xm(nm.y, mat.normal_map_strength);
-                nm = xnormalize(nm);
-                surface_normal = xnormalize(f3(xa(xa(xm(tangent.x, nm.x), xm(bitangent.x, nm.y)), xm(normal.x, nm.z)),
+                nm = xnormalize_s(nm);
+                surface_normal = xnormalize_s(f3(xa(xa(xm(tangent.x, nm.x), xm(bitangent.x, nm.y)), xm(normal.x, nm.z)),
                                                xa(xa(xm(tangent.y, nm.x), xm(bitangent.y, nm.y)), xm(normal.y, nm.z)),
                                                xa(xa(xm(tangent.z, nm.x), xm(bitangent.z, nm.y)), xm(normal.z, nm.z))));
             }
@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(kShadeBlock, RTX_SHADE_MIN_BLOCKS) shade_kerne
             bool emit = false; float3 sdir = f3(0, 0, 1), c = f3(0, 0, 0); float len = 3.402823466e+38f;
             if (hit) {
                 const float3 lpos = f3(L.pos[0], L.pos[1], L.pos[2]), ldir = f3(L.dir[0], L.dir[1], L.dir[2]);
-                const float3 dtl = L.type == 0 ? xnormalize(xneg(ldir)) : xnormalize(xsub(lpos, hit_point));
+                const float3 dtl = L.type == 0 ? xnormalize_s(xneg(ldir)) : xnormalize_s(xsub(lpos, hit_point));
                 const float dot_light = fmaxf(dot3(surface_normal, dtl), 0.0f);
                 const float3 mi = -dtl;
                 const float3 reflect_dir = mi - (2.0f * dot3(surface_normal, mi)) * surface_normal;
@@ -459,7 +459,7 @@ __global__ void __launch_bounds__(kShadeBlock, RTX_SHADE_MIN_BLOCKS) shade_kerne
             const uint32_t slot = queue_append(out.child_count, emit_refl);
             if (emit_refl) {
                 if (slot < out.child_cap) {
-                    const float3 nd = xnormalize(refl_d);                         // :722-723 of the recursive call
+                    const float3 nd = xnormalize_s(refl_d);                         // :722-723 of the recursive call
                     out.child.o[slot] = make_float4(refl_o.x, refl_o.y, refl_o.z, w_refl);
                     out.child.d[slot] = make_float4(nd.x, nd.y, nd.z, __uint_as_float(pixel));
                     out.child.m[slot] = make_uint2(sample | ((depth + 1) << 16), path * 2u);
@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(kShadeBlock, RTX_SHADE_MIN_BLOCKS) shade_kerne
             const uint32_t slot = queue_append(out.child_count, emit_trans);
             if (emit_trans) {
                 if (slot < out.child_cap) {
-                    const float3 nd = xnormalize(trans_d);
+                    const float3 nd = xnormalize_s(trans_d);
                     out.child.o[slot] = make_float4(trans_o.x, trans_o.y, trans_o.z, w_trans);
                     out.child.d[slot] = make_float4(nd.x, nd.y, nd.z, __uint_as_float(pixel));
                     out.child.m[slot] = make_uint2(sample | ((depth + 1) << 16) | (trans_flags << 24), path * 2u + 1u);
