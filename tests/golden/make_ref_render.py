@@ -1,4 +1,5 @@
-"""Downsample the author's rendering of config 2 (a real output of the reference) into a small fixture.
+"""Downsample two of the author's renderings (real outputs of the reference) into small fixtures: config 2
+(floor + monkey) and the room of glass / mirror spheres (room-no-textures.json + spheres.json).
     python tests/golden/make_ref_render.py [/root/reference]"""
 import os
 import sys
@@ -14,3 +15,10 @@ assert im.shape == (720, 1280, 3)
 small = im.reshape(180, 4, 320, 4, 3).mean(axis=(1, 3))
 Image.fromarray(np.clip(small + 0.5, 0, 255).astype(np.uint8)).save(os.path.join(HERE, "ref_render_c2_320x180.png"))
 print("wrote ref_render_c2_320x180.png")
+
+src = os.path.join(ref, "data", "renderings", "output_2022-5-16_21-24-33_00000000.png")
+im = np.asarray(Image.open(src).convert("RGB")).astype(np.float32)
+assert im.shape == (720, 1280, 3)
+small = im.reshape(180, 4, 320, 4, 3).mean(axis=(1, 3))
+Image.fromarray(np.clip(small + 0.5, 0, 255).astype(np.uint8)).save(os.path.join(HERE, "ref_render_room_spheres_320x180.png"))
+print("wrote ref_render_room_spheres_320x180.png")

@@ -300,3 +300,22 @@ def test_author_rendering_of_config2_pins_the_oracle():
     img = f.image[..., :3].astype(np.float32).reshape(180, 2, 320, 2, 3).mean(axis=(1, 3))
     p = psnr(img, ref)
     assert p >= 30.0, p
+
+
+def test_author_rendering_of_the_sphere_room_pins_ball_semantics():
+    """Second reference OUTPUT: the author's rendering of the room of glass / mirror / textured spheres
+    (data/renderings/output_2022-5-16_21-24-33_00000000.png = scene/room-no-textures.json + scene/spheres.json,
+    committed 4x downsampled).  It exercises what config 2 does not: Ball ray casts from outside and inside, refraction
+    through spheres, the mirror recursion between walls.  The oracle's Monte-Carlo render must reach PSNR >= 30 dB, and the
+    one third-party detail that cannot be checked offline (parry's Ball normal when the ray starts inside: negated, the
+    default here, vs outward) must not score worse than the alternative."""
+    from PIL import Image
+    ref = np.asarray(Image.open(os.path.join(HERE, "golden", "ref_render_room_spheres_320x180.png")).convert("RGB")).astype(np.float32)
+    fs, cam, cfg = abi.load_fixture("room_spheres", samples=16, monte_carlo=1)
+    cam = abi.resize_camera(cam, 320, 180)
+    score = {}
+    for outward in (0, 1):
+        r = OracleRenderer(fs)
+        r.set_options(ball_normal_outward_inside=outward)
+        score[outward] = psnr(r.render(cam, cfg).image[..., :3].astype(np.float32), ref)
+    assert score[0] >= 30.0 and score[0] >= score[1], score
