@@ -225,6 +225,12 @@ int rtx_render_frame_async(RtxScene* scene, const RtxCamera* cam, const RtxConfi
                            uint8_t* rgba, float* normals, float* depth, uint32_t* object_ids);
 int rtx_render_poll(RtxScene* scene, uint64_t* pixels_rendered, int* running, int* done, int* result, RtxStats* stats);
 int rtx_render_stop(RtxScene* scene);
+/* Progressive display (the reference streams finished pixels to the window through an mpsc channel, src/renderer.rs:
+ * 305-312 -> src/run.rs:506-545): while an async frame is in flight, refresh ITS host buffers with the current state —
+ * pixels whose samples have all been issued are normalised by the sample count, the pixel range in progress by the samples
+ * issued so far, untouched pixels are zero.  Returns after the buffers were written (at the next wave boundary), or at once
+ * when no frame is running (the buffers then hold the finished frame).  *pixels_rendered as in rtx_render_poll. */
+int rtx_render_snapshot(RtxScene* scene, uint64_t* pixels_rendered);
 
 /* Same frame, DEVICE output buffers (same layouts) on the scene's device, restricted to the
  * pixels of `shard` (NULL = whole frame); pixels of other ranks are left untouched.

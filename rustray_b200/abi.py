@@ -289,6 +289,7 @@ def bind(lib: C.CDLL, prefix: str = "rtx_") -> None:
         "render_frame_async": (C.c_int, [C.c_void_p, P(RtxCamera), P(RtxConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
         "render_poll": (C.c_int, [C.c_void_p, P(C.c_uint64), P(C.c_int), P(C.c_int), P(C.c_int), P(RtxStats)]),
         "render_stop": (C.c_int, [C.c_void_p]),
+        "render_snapshot": (C.c_int, [C.c_void_p, P(C.c_uint64)]),
         "trace_probe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_uint32, C.c_void_p]),
         "sample_table": (C.c_int, [C.c_uint32, P(C.c_uint32), C.c_void_p]),
         "scene_bvh_info": (C.c_int, [C.c_void_p, P(RtxBvhInfo)]),
@@ -307,7 +308,7 @@ def bind(lib: C.CDLL, prefix: str = "rtx_") -> None:
 
 
 ABI_SYMBOLS = ["rtx_scene_create", "rtx_scene_update_items", "rtx_scene_set_lights", "rtx_render_frame",
-               "rtx_render_frame_device", "rtx_render_frame_async", "rtx_render_poll", "rtx_render_stop", "rtx_shard_pixel_count", "rtx_shard_packed_bytes", "rtx_shard_pack",
+               "rtx_render_frame_device", "rtx_render_frame_async", "rtx_render_poll", "rtx_render_stop", "rtx_render_snapshot", "rtx_shard_pixel_count", "rtx_shard_packed_bytes", "rtx_shard_pack",
                "rtx_shard_unpack", "rtx_trace_probe", "rtx_sample_table", "rtx_scene_bvh_info",
                "rtx_scene_destroy", "rtx_last_error", "rtx_abi_version", "rtx_device_count",
                "rtx_post_process_device"]

@@ -19,6 +19,8 @@
 #include <map>
 #include <string>
 #include <thread>
+#include <condition_variable>
+#include <mutex>
 #include <tuple>
 #include <vector>
 
@@ -103,6 +105,9 @@ struct RtxScene {
     // async frame (RendererManager::start / stop / is_done)
     std::thread worker; std::atomic<bool> running{false}, cancel{false}; std::atomic<uint64_t> samples_issued{0};
     uint64_t async_pixels = 0; uint32_t async_samples = 1; int async_result = RTX_OK; RtxStats async_stats{}; std::string async_err;
+    // progressive preview of the frame in flight (rtx_render_snapshot): host targets of the async frame + request/ack
+    uint8_t* snap_rgba = nullptr; float* snap_normals = nullptr; float* snap_depth = nullptr; uint32_t* snap_ids = nullptr;
+    std::atomic<uint32_t> snap_req{0}; std::mutex snap_mu; std::condition_variable snap_cv; uint64_t snap_seq = 0;
 };
 
 namespace {
@@ -640,6 +645,32 @@ int rtx_render_frame_device(RtxScene* sc, const RtxCamera* cam, const RtxConfig*
 
     for (;;) {
         if (sc->cancel.load(std::memory_order_relaxed)) { CU(cudaStreamSynchronize(st)); return fail(RTX_E_CANCELLED, "frame cancelled by rtx_render_stop"); }
+        if (sc->snap_req.load(std::memory_order_relaxed)) {
+            // progressive preview (the stream is idle here): pixels whose samples were all issued are normalised by the sample
+            // count, the pixel range in progress by the samples issued so far, the rest is cleared; rays still queued at
+            // deeper levels are simply not in the sums yet
+            const size_t npx = (size_t)cam->width * cam->height;
+            if (d_rgba) CU(cudaMemsetAsync(d_rgba, 0, npx * 4, st));
+            if (d_normals) CU(cudaMemsetAsync(d_normals, 0, npx * 12, st));
+            if (d_depth) CU(cudaMemsetAsync(d_depth, 0, npx * 4, st));
+            if (d_object_ids) CU(cudaMemsetAsync(d_object_ids, 0, npx * 4, st));
+            const uint32_t done_px = primary_left ? cur_p0 : pl->n;
+            if (done_px) resolve_kernel<<<std::min<uint32_t>((done_px + 255) / 256, gs), 256, 0, st>>>(F, pl->d.p, done_px, (uchar4*)d_rgba, (float*)d_normals,
+                                                                                                    (float*)d_depth, (uint32_t*)d_object_ids);
+            if (primary_left && cur_s0 > 0) {
+                FrameDev Fp = F; Fp.n_samples = cur_s0;
+                const uint32_t np = std::min(np_full, pl->n - cur_p0);
+                resolve_kernel<<<std::min<uint32_t>((np + 255) / 256, gs), 256, 0, st>>>(Fp, pl->d.p + cur_p0, np, (uchar4*)d_rgba, (float*)d_normals, (float*)d_depth,
+                                                                                       (uint32_t*)d_object_ids);
+            }
+            if (sc->snap_rgba && d_rgba) CU(cudaMemcpyAsync(sc->snap_rgba, d_rgba, npx * 4, cudaMemcpyDeviceToHost, st));
+            if (sc->snap_normals && d_normals) CU(cudaMemcpyAsync(sc->snap_normals, d_normals, npx * 12, cudaMemcpyDeviceToHost, st));
+            if (sc->snap_depth && d_depth) CU(cudaMemcpyAsync(sc->snap_depth, d_depth, npx * 4, cudaMemcpyDeviceToHost, st));
+            if (sc->snap_ids && d_object_ids) CU(cudaMemcpyAsync(sc->snap_ids, d_object_ids, npx * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            { std::lock_guard<std::mutex> lk(sc->snap_mu); sc->snap_seq++; sc->snap_req.store(0); }
+            sc->snap_cv.notify_all();
+        }
         int level = -1;
         for (int d = (int)L; d >= 1; d--) if (counts[d] >= chunk) { level = d; break; }
         if (level < 0 && primary_left) level = 0;
@@ -791,12 +822,14 @@ int rtx_render_frame_async(RtxScene* sc, const RtxCamera* cam, const RtxConfig* 
     sc->cancel.store(false); sc->samples_issued.store(0);
     sc->async_pixels = (uint64_t)cam->width * cam->height; sc->async_samples = std::max(1u, cfg->samples);
     sc->async_result = RTX_OK; sc->running.store(true);
+    sc->snap_rgba = rgba; sc->snap_normals = normals; sc->snap_depth = depth; sc->snap_ids = object_ids; sc->snap_req.store(0);
     const RtxCamera c = *cam; const RtxConfig g = *cfg;
     sc->worker = std::thread([=]() {
         int rc = rtx_render_frame(sc, &c, &g, rgba, normals, depth, object_ids, &sc->async_stats);
         sc->async_result = rc;
         if (rc) sc->async_err = g_err;                                    // g_err is thread-local: keep the worker's message
-        sc->running.store(false, std::memory_order_release);
+        { std::lock_guard<std::mutex> lk(sc->snap_mu); sc->running.store(false, std::memory_order_release); sc->snap_req.store(0); }
+        sc->snap_cv.notify_all();                                         // a snapshot waiting on a finished frame sees the final buffers
     });
     return RTX_OK;
 }
@@ -815,6 +848,19 @@ int rtx_render_poll(RtxScene* sc, uint64_t* pixels_rendered, int* running, int* 
     if (!run && sc->async_result != RTX_OK) g_err = sc->async_err;
     if (stats && !run) *stats = sc->async_stats;
     return RTX_OK;
+}
+
+int rtx_render_snapshot(RtxScene* sc, uint64_t* pixels_rendered) {
+    if (!sc) return fail(RTX_E_INVALID, "null argument");
+    {
+        std::unique_lock<std::mutex> lk(sc->snap_mu);
+        if (sc->running.load(std::memory_order_acquire)) {
+            const uint64_t seq = sc->snap_seq;
+            sc->snap_req.store(1);
+            sc->snap_cv.wait(lk, [&]() { return sc->snap_seq != seq || !sc->running.load(std::memory_order_acquire); });
+        }
+    }
+    return rtx_render_poll(sc, pixels_rendered, nullptr, nullptr, nullptr, nullptr);
 }
 
 int rtx_render_stop(RtxScene* sc) {

@@ -180,6 +180,13 @@ class RendererManager(AbiRenderer):
             return self._poll()[0]
         return self.width * self.height if self._done else 0
 
+    def snapshot(self) -> int:
+        """Progressive display (the per-pixel mpsc stream of src/renderer.rs:305-312 -> src/run.rs:506-545): refresh
+        `self.frame` with the current state of the frame in flight; returns get_rendered_pixels()."""
+        px = C.c_uint64()
+        self._check(self._lib.rtx_render_snapshot(self._h, C.byref(px)))
+        return int(px.value)
+
     def stop(self) -> None:                  # src/renderer.rs:174-199
         self._check(self._lib.rtx_render_stop(self._h))
 

@@ -322,6 +322,50 @@ def test_async_frame_progress_and_stop():
     assert lsb_stats(g.start(cam, cfg).image, want)[0] >= 0.9999
 
 
+def test_progressive_snapshots_of_a_frame_in_flight():
+    """'next' row 4, progressive display: rtx_render_snapshot refreshes the host buffers of the async frame with what is
+    accumulated so far.  Snapshots must get monotonically more complete, a snapshot after the end is the final frame, and
+    taking snapshots must not change the result."""
+    import time
+    fs, cam, cfg = abi.load_fixture("room_spheres", samples=256, monte_carlo=1, mc_seed=3)
+    cam = abi.resize_camera(cam, 640, 360)
+    g = RendererManager(640, 360, fs)
+    want = g.start(cam, cfg).image.copy()
+    g.frame.image[:] = 0
+    g.start_async(cam, cfg)
+    means, pixels = [], []
+    while g.is_running():
+        pixels.append(g.snapshot())
+        means.append(float(g.frame.image[..., :3].mean()))
+        time.sleep(0.01)
+    assert len(means) >= 3, len(means)                                 # the 256-spp frame takes many waves
+    mid = [m for m in means[:-1] if m > 0]
+    # normalised by the samples issued so far, not by the total (the first snapshot comes after ~9 of 256 samples: 3.5 %);
+    # rays still queued at deeper levels (this room is all mirrors) are missing, so it is darker than the final frame
+    assert mid and min(mid) > 0.15 * float(want[..., :3].mean()), (means, float(want[..., :3].mean()))
+    assert pixels == sorted(pixels)
+    assert g.snapshot() == 640 * 360 and g.is_done()
+    assert lsb_stats(g.frame.image, want)[0] >= 0.9999                 # float atomics: sums are order-dependent in the last bit
+    # a frame with more pixels than one wave holds is rendered pixel range by pixel range: snapshots in between show
+    # finished ranges + cleared rest, and the final buffers equal the blocking render
+    fs2, cam2, cfg2 = abi.load_fixture("c1_spheres", samples=4, monte_carlo=0)
+    cam2 = abi.resize_camera(cam2, 4096, 3072)
+    g2 = RendererManager(4096, 3072, fs2)
+    want2 = g2.start(cam2, cfg2).objects.copy()
+    g2.frame.objects[:] = 0
+    g2.start_async(cam2, cfg2)
+    partial = 0
+    while g2.is_running():
+        px = g2.snapshot()
+        if 0 < px < 4096 * 3072:
+            ids = g2.frame.objects
+            partial += 1
+            assert np.isin(ids, np.concatenate([[0], np.unique(want2)])).all()
+            assert ((ids != 0) & (ids != want2)).sum() == 0             # what is there is final (ids are written by the last sample)
+        time.sleep(0.002)
+    assert g2.is_done() and np.array_equal(g2.frame.objects, want2)
+
+
 def test_error_codes_instead_of_panics():
     fs, cam, cfg = abi.load_fixture("c1_spheres")
     g = RendererManager(16, 16, fs)
