@@ -788,6 +788,13 @@ int rtx_render_frame_device(RtxScene* sc, const RtxCamera* cam, const RtxConfig*
         stats->rays_shadow_skipped = ovf[2]; stats->rays_shadow += ovf[2];
         if (want_stats) {
             Counters c; CU(cudaMemcpy(&c, sc->counters.p, sizeof(c), cudaMemcpyDeviceToHost));
+            if (getenv("RTX_PHASE_STATS"))
+                for (int k = 0; k < 2; k++) {
+                    const unsigned long long* p = c.phase[k];
+                    fprintf(stderr, "[phase %s] steps/warp-steps %llu | lanes with a ray %.1f/32 | NODE lanes %.1f/32 | LEAF rounds %.2f per step, lanes %.1f/32 | refills %llu, lanes %.1f\n",
+                            k ? "shadow" : "closest", p[0], (double)p[1] / std::max(1ull, p[0]), (double)p[2] / std::max(1ull, p[0]), (double)p[3] / std::max(1ull, p[0]),
+                            (double)p[4] / std::max(1ull, p[3]), p[5], (double)p[6] / std::max(1ull, p[5]));
+                }
             stats->node_visits[0] = c.node_visits[0]; stats->node_visits[1] = c.node_visits[1];
             stats->tri_tests[0] = c.tri_tests[0]; stats->tri_tests[1] = c.tri_tests[1];
             stats->sphere_tests = c.sphere_tests; stats->item_tests = c.item_tests;

@@ -94,6 +94,10 @@ enum : uint32_t { RF_ID_OWNER = 1u };
 
 struct Counters {      // device counters, 64-bit
     unsigned long long node_visits[2], tri_tests[2], sphere_tests, item_tests;   // [0] closest kernel, [1] shadow kernel
+    // lane utilisation of the step loop (STATS kernels only; printed with RTX_PHASE_STATS=1): per kernel
+    // [0] steps (per warp)  [1] lanes with a ray, summed over steps  [2] lanes in the NODE phase  [3] LEAF rounds  [4] lanes in LEAF rounds
+    // [5] refills  [6] lanes refilled
+    unsigned long long phase[2][8];
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -709,13 +713,16 @@ __device__ __forceinline__ void lane_any_hit(Lane& L, float key, uint32_t item) 
     L.ng = make_uint2(0u, 0u); L.tg = make_uint2(0u, 0u);
 }
 
-template <int MODE, bool STATS>
+// WHICH: 0 = whatever the entry is; 1 = the caller knows it is a triangle (L.blas_base >= 0); 2 = an item of the TLAS.
+// The kernels run triangles and items in separate rounds: the two paths share no code, so a mixed round would execute
+// both at a fraction of the lanes each.
+template <int MODE, bool STATS, int WHICH = 0>
 __device__ __forceinline__ void lane_leaf(Lane& L, uint2* stack, const SceneDev& S, bool for_shadow, uint32_t depth,
                                           TravStats& st, uint32_t& n_items, uint32_t& n_sph) {
     const uint32_t ti = bfind(L.tg.y);
     L.tg.y &= ~(1u << ti);
     const uint32_t prim = L.tg.x + ti;
-    if (L.blas_base >= 0) {                                               // triangle of the current item
+    if (WHICH == 1 || (WHICH == 0 && L.blas_base >= 0)) {                 // triangle of the current item
         const float4* tp = S.tris + (size_t)prim * 3;
         const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
         if (STATS) st.tris++;

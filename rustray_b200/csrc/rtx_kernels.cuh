@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256) raygen_kernel(FrameDev F, const uint32_t*
 #define RTX_MIN_BLOCKS 7
 #endif
 #ifndef RTX_LEAF_BATCH
-#define RTX_LEAF_BATCH 8
+#define RTX_LEAF_BATCH 6
 #endif
 #ifndef RTX_NODE_REPS
 #define RTX_NODE_REPS 1
@@ -100,17 +100,26 @@ constexpr int kNodeReps = RTX_NODE_REPS;   // node phases per loop iteration
 constexpr int kRefill = RTX_REFILL;        // refill the warp when fewer lanes than this still own a ray
 constexpr int kLeafBatch = RTX_LEAF_BATCH;  // run a leaf phase when at least this many lanes have pending leaf entries
 constexpr uint32_t kFull = 0xffffffffu;
+#ifndef RTX_SPLIT_LEAF
+#define RTX_SPLIT_LEAF 1                    // triangles and TLAS items in separate LEAF rounds, each with its own threshold
+#endif
+#ifndef RTX_ITEM_BATCH
+#define RTX_ITEM_BATCH 4
+#endif
+constexpr int kItemBatch = RTX_ITEM_BATCH;
 
 template <bool STATS>
 __global__ void __launch_bounds__(kTraceBlock, RTX_MIN_BLOCKS) closest_kernel(SceneDev S, RayQ q, uint32_t q_base, uint32_t n, HitRec* __restrict__ hits,
                                                               uint32_t* work, Counters* ctr) {
     TravStats st{0, 0}; uint32_t n_items = 0, n_sph = 0;
+    uint32_t ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint2 stack[kLaneStack];
     Lane L; bool has = false, exhausted = false; uint32_t my = 0, depth = 1;
     const uint32_t lane = threadIdx.x & 31u;
     for (;;) {
         const uint32_t idle = __ballot_sync(kFull, !has);
         if (idle != 0u && !exhausted) {
+            if (STATS) { ph[5] += (lane == 0); ph[6] += !has; }
             const uint32_t leader = __ffs(idle) - 1u, cnt = __popc(idle);
             uint32_t base = 0;
             if (lane == leader) base = atomicAdd(work, cnt);
@@ -135,14 +144,32 @@ __global__ void __launch_bounds__(kTraceBlock, RTX_MIN_BLOCKS) closest_kernel(Sc
                 if (has && L.ng.y > 0x00FFFFFFu) lane_node<UT_CLOSEST, STATS>(L, stack, S, st);
                 if (has && L.ng.y <= 0x00FFFFFFu && L.tg.y == 0u && L.sp != 0 && !(L.blas_base >= 0 && L.sp == L.blas_base)) lane_pop(L, stack);
             }
+            if (STATS) { ph[0] += (lane == 0); ph[1] += has; ph[2] += (has && L.ng.y > 0x00FFFFFFu); }
             if (has && L.ng.y > 0x00FFFFFFu) lane_node<UT_CLOSEST, STATS>(L, stack, S, st);
+#if RTX_SPLIT_LEAF
+            {
+                const bool want_tri = has && L.tg.y != 0u && L.blas_base >= 0, want_item = has && L.tg.y != 0u && L.blas_base < 0;
+                const uint32_t mt = __ballot_sync(kFull, want_tri), mi = __ballot_sync(kFull, want_item);
+                const bool no_nodes = !__any_sync(kFull, has && L.ng.y > 0x00FFFFFFu);
+                if (mt != 0u && (__popc(mt) >= kLeafBatch || no_nodes)) {
+                    if (STATS) { ph[3] += (lane == 0); ph[4] += want_tri; }
+                    if (want_tri) lane_leaf<UT_CLOSEST, STATS, 1>(L, stack, S, false, depth, st, n_items, n_sph);
+                }
+                if (mi != 0u && (__popc(mi) >= kItemBatch || no_nodes)) {
+                    if (STATS) { ph[3] += (lane == 0); ph[4] += want_item; }
+                    if (want_item) lane_leaf<UT_CLOSEST, STATS, 2>(L, stack, S, false, depth, st, n_items, n_sph);
+                }
+            }
+#else
             {
                 const bool want_leaf = has && L.tg.y != 0u;
                 const uint32_t ml = __ballot_sync(kFull, want_leaf);
                 if (ml != 0u && (__popc(ml) >= kLeafBatch || !__any_sync(kFull, has && L.ng.y > 0x00FFFFFFu))) {
+                    if (STATS) { ph[3] += (lane == 0); ph[4] += want_leaf; }
                     if (want_leaf) lane_leaf<UT_CLOSEST, STATS>(L, stack, S, false, depth, st, n_items, n_sph);
                 }
             }
+#endif
             if (has && L.ng.y <= 0x00FFFFFFu && L.tg.y == 0u && lane_pop(L, stack)) {
                 HitRec h; h.t = L.tmax; h.item = L.bitem; h.prim = L.bprim; h.flags = L.bflags;
                 hits[my] = h;
@@ -155,6 +182,7 @@ __global__ void __launch_bounds__(kTraceBlock, RTX_MIN_BLOCKS) closest_kernel(Sc
     if (STATS) {
         atomicAdd(&ctr->node_visits[0], (unsigned long long)st.nodes); atomicAdd(&ctr->tri_tests[0], (unsigned long long)st.tris);
         atomicAdd(&ctr->item_tests, (unsigned long long)n_items); atomicAdd(&ctr->sphere_tests, (unsigned long long)n_sph);
+        for (int k = 0; k < 7; k++) atomicAdd(&ctr->phase[0][k], (unsigned long long)ph[k]);
     }
 }
 
@@ -168,6 +196,7 @@ template <bool STATS>
 __global__ void __launch_bounds__(kTraceBlock, RTX_MIN_BLOCKS) shadow_any_kernel(SceneDev S, FrameDev F, ShadowQ q, const uint32_t* __restrict__ n_ptr, uint32_t depth,
                                                                  uint32_t* work, uint32_t* __restrict__ slow, uint32_t* slow_count, Counters* ctr) {
     TravStats st{0, 0}; uint32_t n_items = 0, n_sph = 0;
+    uint32_t ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint2 stack[kLaneStack];
     Lane L; bool has = false, exhausted = false; uint32_t my = 0;
     const uint32_t lane = threadIdx.x & 31u;
@@ -175,6 +204,7 @@ __global__ void __launch_bounds__(kTraceBlock, RTX_MIN_BLOCKS) shadow_any_kernel
     for (;;) {
         const uint32_t idle = __ballot_sync(kFull, !has);
         if (idle != 0u && !exhausted) {
+            if (STATS) { ph[5] += (lane == 0); ph[6] += !has; }
             const uint32_t leader = __ffs(idle) - 1u, cnt = __popc(idle);
             uint32_t base = 0;
             if (lane == leader) base = atomicAdd(work, cnt);
@@ -198,14 +228,32 @@ __global__ void __launch_bounds__(kTraceBlock, RTX_MIN_BLOCKS) shadow_any_kernel
                 if (has && L.ng.y > 0x00FFFFFFu) lane_node<UT_ANY, STATS>(L, stack, S, st);
                 if (has && L.ng.y <= 0x00FFFFFFu && L.tg.y == 0u && L.sp != 0 && !(L.blas_base >= 0 && L.sp == L.blas_base)) lane_pop(L, stack);
             }
+            if (STATS) { ph[0] += (lane == 0); ph[1] += has; ph[2] += (has && L.ng.y > 0x00FFFFFFu); }
             if (has && L.ng.y > 0x00FFFFFFu) lane_node<UT_ANY, STATS>(L, stack, S, st);
+#if RTX_SPLIT_LEAF
+            {
+                const bool want_tri = has && L.tg.y != 0u && L.blas_base >= 0, want_item = has && L.tg.y != 0u && L.blas_base < 0;
+                const uint32_t mt = __ballot_sync(kFull, want_tri), mi = __ballot_sync(kFull, want_item);
+                const bool no_nodes = !__any_sync(kFull, has && L.ng.y > 0x00FFFFFFu);
+                if (mt != 0u && (__popc(mt) >= kLeafBatch || no_nodes)) {
+                    if (STATS) { ph[3] += (lane == 0); ph[4] += want_tri; }
+                    if (want_tri) lane_leaf<UT_ANY, STATS, 1>(L, stack, S, true, depth, st, n_items, n_sph);
+                }
+                if (mi != 0u && (__popc(mi) >= kItemBatch || no_nodes)) {
+                    if (STATS) { ph[3] += (lane == 0); ph[4] += want_item; }
+                    if (want_item) lane_leaf<UT_ANY, STATS, 2>(L, stack, S, true, depth, st, n_items, n_sph);
+                }
+            }
+#else
             {
                 const bool want_leaf = has && L.tg.y != 0u;
                 const uint32_t ml = __ballot_sync(kFull, want_leaf);
                 if (ml != 0u && (__popc(ml) >= kLeafBatch || !__any_sync(kFull, has && L.ng.y > 0x00FFFFFFu))) {
+                    if (STATS) { ph[3] += (lane == 0); ph[4] += want_leaf; }
                     if (want_leaf) lane_leaf<UT_ANY, STATS>(L, stack, S, true, depth, st, n_items, n_sph);
                 }
             }
+#endif
             bool to_slow = false;
             if (has && L.ng.y <= 0x00FFFFFFu && L.tg.y == 0u && lane_pop(L, stack)) {
                 has = false;
@@ -233,6 +281,7 @@ __global__ void __launch_bounds__(kTraceBlock, RTX_MIN_BLOCKS) shadow_any_kernel
     if (STATS) {
         atomicAdd(&ctr->node_visits[1], (unsigned long long)st.nodes); atomicAdd(&ctr->tri_tests[1], (unsigned long long)st.tris);
         atomicAdd(&ctr->item_tests, (unsigned long long)n_items); atomicAdd(&ctr->sphere_tests, (unsigned long long)n_sph);
+        for (int k = 0; k < 7; k++) atomicAdd(&ctr->phase[1][k], (unsigned long long)ph[k]);
     }
 }
 
