@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256) raygen_kernel(FrameDev F, const uint32_t*
 #define RTX_MIN_BLOCKS 7
 #endif
 #ifndef RTX_LEAF_BATCH
-#define RTX_LEAF_BATCH 6
+#define RTX_LEAF_BATCH 8
 #endif
 #ifndef RTX_NODE_REPS
 #define RTX_NODE_REPS 1
@@ -107,6 +107,9 @@ constexpr uint32_t kFull = 0xffffffffu;
 #define RTX_ITEM_BATCH 4
 #endif
 constexpr int kItemBatch = RTX_ITEM_BATCH;
+#ifndef RTX_TRI_REPS
+#define RTX_TRI_REPS 2                      // triangles handled per lane in one triangle round
+#endif
 
 template <bool STATS>
 __global__ void __launch_bounds__(kTraceBlock, RTX_MIN_BLOCKS) closest_kernel(SceneDev S, RayQ q, uint32_t q_base, uint32_t n, HitRec* __restrict__ hits,
@@ -153,7 +156,12 @@ __global__ void __launch_bounds__(kTraceBlock, RTX_MIN_BLOCKS) closest_kernel(Sc
                 const bool no_nodes = !__any_sync(kFull, has && L.ng.y > 0x00FFFFFFu);
                 if (mt != 0u && (__popc(mt) >= kLeafBatch || no_nodes)) {
                     if (STATS) { ph[3] += (lane == 0); ph[4] += want_tri; }
-                    if (want_tri) lane_leaf<UT_CLOSEST, STATS, 1>(L, stack, S, false, depth, st, n_items, n_sph);
+                    if (want_tri) {
+                        lane_leaf<UT_CLOSEST, STATS, 1>(L, stack, S, false, depth, st, n_items, n_sph);
+#pragma unroll
+                        for (int rep = 1; rep < RTX_TRI_REPS; rep++)
+                            if (L.tg.y != 0u && L.blas_base >= 0) lane_leaf<UT_CLOSEST, STATS, 1>(L, stack, S, false, depth, st, n_items, n_sph);
+                    }
                 }
                 if (mi != 0u && (__popc(mi) >= kItemBatch || no_nodes)) {
                     if (STATS) { ph[3] += (lane == 0); ph[4] += want_item; }
@@ -237,7 +245,12 @@ __global__ void __launch_bounds__(kTraceBlock, RTX_MIN_BLOCKS) shadow_any_kernel
                 const bool no_nodes = !__any_sync(kFull, has && L.ng.y > 0x00FFFFFFu);
                 if (mt != 0u && (__popc(mt) >= kLeafBatch || no_nodes)) {
                     if (STATS) { ph[3] += (lane == 0); ph[4] += want_tri; }
-                    if (want_tri) lane_leaf<UT_ANY, STATS, 1>(L, stack, S, true, depth, st, n_items, n_sph);
+                    if (want_tri) {
+                        lane_leaf<UT_ANY, STATS, 1>(L, stack, S, true, depth, st, n_items, n_sph);
+#pragma unroll
+                        for (int rep = 1; rep < RTX_TRI_REPS; rep++)
+                            if (L.tg.y != 0u && L.blas_base >= 0) lane_leaf<UT_ANY, STATS, 1>(L, stack, S, true, depth, st, n_items, n_sph);
+                    }
                 }
                 if (mi != 0u && (__popc(mi) >= kItemBatch || no_nodes)) {
                     if (STATS) { ph[3] += (lane == 0); ph[4] += want_item; }
