@@ -206,10 +206,33 @@ __global__ void __launch_bounds__(kTraceBlock, RTX_MIN_BLOCKS) shadow_any_kernel
     TravStats st{0, 0}; uint32_t n_items = 0, n_sph = 0;
     uint32_t ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint2 stack[kLaneStack];
-    Lane L; bool has = false, exhausted = false; uint32_t my = 0;
+    Lane L; bool has = false, exhausted = false, fin = false; uint32_t my = 0;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = *n_ptr;
     for (;;) {
+        // write-back of the rays that ended since the last refill, all at once (the lanes that are about to be refilled)
+        {
+            bool to_slow = false;
+            if (fin) {
+                fin = false;
+                const bool occluded = L.bitem != 0xFFFFFFFFu;
+                const float okey = __uint_as_float(L.bprim);
+                const bool earlier_other = L.bface != 0xFFFFFFFFu && (okey < L.bkey || (okey == L.bkey && L.bface < L.bitem));
+                if (!occluded || (!S.any_alpha_tex && (L.tmax >= 3.402823466e+38f || !earlier_other))) {
+                    const float4 rc = q.c[my];
+                    const float k = occluded ? 1.0f - rc.w : 1.0f;               // raytracing.rs:898,912
+                    atomicAdd(&F.accum_c[__float_as_uint(q.d[my].w)], make_float4(rc.x * k, rc.y * k, rc.z * k, 0.0f));
+                } else to_slow = true;
+            }
+            const uint32_t sm = __ballot_sync(kFull, to_slow);
+            if (sm != 0u) {
+                const uint32_t leader = __ffs(sm) - 1u;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(slow_count, __popc(sm));
+                base = __shfl_sync(kFull, base, leader);
+                if (to_slow) slow[base + __popc(sm & ((1u << lane) - 1u))] = my;
+            }
+        }
         const uint32_t idle = __ballot_sync(kFull, !has);
         if (idle != 0u && !exhausted) {
             if (STATS) { ph[5] += (lane == 0); ph[6] += !has; }
@@ -267,26 +290,7 @@ __global__ void __launch_bounds__(kTraceBlock, RTX_MIN_BLOCKS) shadow_any_kernel
                 }
             }
 #endif
-            bool to_slow = false;
-            if (has && L.ng.y <= 0x00FFFFFFu && L.tg.y == 0u && lane_pop(L, stack)) {
-                has = false;
-                const bool occluded = L.bitem != 0xFFFFFFFFu;
-                const float okey = __uint_as_float(L.bprim);
-                const bool earlier_other = L.bface != 0xFFFFFFFFu && (okey < L.bkey || (okey == L.bkey && L.bface < L.bitem));
-                if (!occluded || (!S.any_alpha_tex && (L.tmax >= 3.402823466e+38f || !earlier_other))) {
-                    const float4 rc = q.c[my];
-                    const float k = occluded ? 1.0f - rc.w : 1.0f;               // raytracing.rs:898,912
-                    atomicAdd(&F.accum_c[__float_as_uint(q.d[my].w)], make_float4(rc.x * k, rc.y * k, rc.z * k, 0.0f));
-                } else to_slow = true;
-            }
-            const uint32_t sm = __ballot_sync(kFull, to_slow);
-            if (sm != 0u) {
-                const uint32_t leader = __ffs(sm) - 1u;
-                uint32_t base = 0;
-                if (lane == leader) base = atomicAdd(slow_count, __popc(sm));
-                base = __shfl_sync(kFull, base, leader);
-                if (to_slow) slow[base + __popc(sm & ((1u << lane) - 1u))] = my;
-            }
+            if (has && L.ng.y <= 0x00FFFFFFu && L.tg.y == 0u && lane_pop(L, stack)) { has = false; fin = true; }   // result stays in L until the refill
             const uint32_t act = __ballot_sync(kFull, has);
             if (act == 0u || (!exhausted && __popc(act) < kRefill)) break;
         }
