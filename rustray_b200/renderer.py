@@ -50,12 +50,28 @@ def load_library() -> C.CDLL:
 class Frame:
     """The four buffers of Run (src/run.rs:117-120)."""
 
-    def __init__(self, width: int, height: int):
+    def __init__(self, width: int, height: int, pinned: bool = False):
+        """`pinned`: allocate the buffers in page-locked host memory (through torch) so that the library's device-to-host
+        copies run at full PCIe/C2C rate; falls back to ordinary memory when CUDA is not available."""
         self.width, self.height = width, height
-        self.image = np.zeros((height, width, 4), dtype=np.uint8)
-        self.normals = np.zeros((height, width, 3), dtype=np.float32)
-        self.depth = np.zeros((height, width), dtype=np.float32)
-        self.objects = np.zeros((height, width), dtype=np.uint32)
+        self._pinned = None
+        if pinned:
+            try:
+                import torch
+                if torch.cuda.is_available():
+                    self._pinned = [torch.zeros(shape, dtype=dt, pin_memory=True) for shape, dt in
+                                    (((height, width, 4), torch.uint8), ((height, width, 3), torch.float32),
+                                     ((height, width), torch.float32), ((height, width), torch.int32))]
+            except Exception:
+                self._pinned = None
+        if self._pinned is not None:
+            self.image, self.normals, self.depth = (t.numpy() for t in self._pinned[:3])
+            self.objects = self._pinned[3].numpy().view(np.uint32)
+        else:
+            self.image = np.zeros((height, width, 4), dtype=np.uint8)
+            self.normals = np.zeros((height, width, 3), dtype=np.float32)
+            self.depth = np.zeros((height, width), dtype=np.float32)
+            self.objects = np.zeros((height, width), dtype=np.uint32)
         self.stats = abi.RtxStats()
 
 
@@ -144,7 +160,7 @@ class RendererManager(AbiRenderer):
     def __init__(self, width: int, height: int, flat_scene: abi.FlatScene, device: int = 0):
         super().__init__(load_library(), "rtx_", flat_scene, device)
         self.width, self.height = width, height
-        self.frame = Frame(width, height)
+        self.frame = Frame(width, height, pinned=True)
         self._done = False
 
     # RendererManager::start (src/renderer.rs:105-172) — blocking on the GPU
