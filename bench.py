@@ -41,7 +41,7 @@ S_NODE, S_TRI, S_SPH = 80, 48, 64          # bytes per node visit / triangle tes
 def workload_config(n_gpus):
     return {"workload": "configs[1]: scene/floor.json + scene/monkey.json 1280x720 monte_carlo=1, %d spp per GPU (spp = %d)" % (
         SPP_PER_GPU, SPP_PER_GPU * n_gpus), "width": 1280, "height": 720, "samples": SPP_PER_GPU * n_gpus, "monte_carlo": 1,
-        "triangles": 15746, "items": 2, "lights": 4, "sharding": "interleaved 8x4 tiles, tile t -> rank t % N, one G-buffer gather",
+        "triangles": 15746, "items": 2, "lights": 4, "sharding": "interleaved 8x4 tiles, one per rank in every group of N tiles (rotated per group), one G-buffer gather",
         "l2": "256 MiB buffer written between timed steps (L2 flush)"}
 
 

@@ -152,7 +152,9 @@ typedef struct RtxConfig {
                                          order" walk instead of the equivalent two-phase any-hit     */
 
 /* Interleaved-tile shard of one frame: tile t (row-major over ceil(w/tile_w) x ceil(h/tile_h))
- * belongs to rank t % world.  world = 1 renders everything. */
+ * belongs to rank (t + rot(t / world)) % world with rot(g) = (g * 0x9E3779B1 mod 2^32) >> 16: one tile per rank in every
+ * group of `world` consecutive tiles, rotated per group (balanced and decorrelated from image columns).
+ * world = 1 renders everything. */
 typedef struct RtxShard {
     uint32_t rank, world, tile_w, tile_h;
 } RtxShard;

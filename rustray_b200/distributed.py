@@ -2,8 +2,9 @@
 
 The reference has no distributed path (threads only).  Pixels are independent and the
 scene is read-only during a frame, so the path shards with no data-path collective: the flattened
-scene is replicated on every GPU, tile t (row-major tiles of tile_w x tile_h pixels) belongs to rank
-t % world, each rank renders and resolves its own pixels, and ONE gather per frame brings the packed
+scene is replicated on every GPU, the row-major tiles of tile_w x tile_h pixels are dealt out in groups of
+`world` (one tile per rank and group, rotated per group so that a rank does not keep the same image columns),
+each rank renders and resolves its own pixels, and ONE gather per frame brings the packed
 24 B/pixel G-buffer (rgba8 | normal 3xf32 | depth f32 | id u32) to rank 0, which scatters it into the
 four frame buffers (`torch.distributed.gather` over NCCL on GPUs; the same host logic runs over gloo
 on CPU in the tests with a numpy pack/unpack).
@@ -23,7 +24,10 @@ def shard_pixels(width: int, height: int, rank: int, world: int, tile_w: int = D
     """Frame pixel indices (y*width+x) owned by `rank`, in the order the library renders and packs them
     (must match get_pixel_list in csrc/rtx_api.cu)."""
     tx, ty = (width + tile_w - 1) // tile_w, (height + tile_h - 1) // tile_h
-    t = np.arange(rank, tx * ty, world, dtype=np.int64)
+    g = np.arange((tx * ty + world - 1) // world, dtype=np.int64)               # groups of `world` consecutive tiles
+    rot = ((g * 0x9E3779B1) & 0xFFFFFFFF) >> 16                                  # per-group rotation (shard_rot in csrc/rtx_api.cu)
+    t = g * world + (rank + world - rot % world) % world
+    t = t[t < tx * ty]
     x0, y0 = (t % tx) * tile_w, (t // tx) * tile_h
     dy, dx = np.mgrid[0:tile_h, 0:tile_w]
     x = x0[:, None] + dx.reshape(1, -1)
