@@ -78,6 +78,7 @@ struct FrameDev {
     uint32_t monte_carlo, max_recursion, gamma, mc_seed;
     float focal_length, aperture_size, fog_density, pad0;
     float fog_color[3]; uint32_t debug_flags;
+    uint32_t sample_group;      // raygen: consecutive rays = this many samples of one pixel
     const ushort2* sample_table;
     float4* accum_c;      // per frame pixel: rgb sum, depth sum
     float4* accum_n;      // per frame pixel: normal sum

@@ -67,7 +67,11 @@ __global__ void __launch_bounds__(256) raygen_kernel(FrameDev F, const uint32_t*
                                                      uint32_t ns, RayQ q, uint32_t q_base) {
     const uint32_t n = np * ns;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t s = s0 + i / np, pi = p0 + i % np;
+        // ray order inside the batch: groups of `sg` samples of one pixel are consecutive (sg = 1: pixel-major per sample)
+        const uint32_t sg = F.sample_group;
+        const uint32_t blk = i / (np * sg), rem = i % (np * sg);                 // sample block, position inside it
+        const uint32_t sb = min(sg, ns - blk * sg);                              // samples in this (possibly short, last) block
+        const uint32_t s = s0 + blk * sg + rem % sb, pi = p0 + rem / sb;
         const uint32_t pixel = __ldg(pixel_list + pi);
         const ushort2 xy = F.sample_table[s];
         float3 o, d;
