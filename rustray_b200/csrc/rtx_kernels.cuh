@@ -365,6 +365,8 @@ struct ShadeOut {
 __global__ void __launch_bounds__(kShadeBlock, RTX_SHADE_MIN_BLOCKS) shade_kernel(SceneDev S, FrameDev F, RayQ q, uint32_t q_base, uint32_t n, const HitRec* __restrict__ hits,
                                                             ShadeOut out) {
     const float PI = 3.14159265358979323846f;
+    uint32_t n_enabled = 0;
+    for (uint32_t li = 0; li < S.n_lights; li++) n_enabled += S.lights[li].enabled ? 1u : 0u;
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
         const uint32_t i = base + threadIdx.x;
         const bool active = i < n;
@@ -388,6 +390,20 @@ __global__ void __launch_bounds__(kShadeBlock, RTX_SHADE_MIN_BLOCKS) shade_kerne
         float shininess = 0.0f, mat_alpha = 1.0f, shadow_z_lo = 1.0f; bool recv_shadow = false, mat_mc = false;
         float3 direct = f3(0, 0, 0), constant = f3(0, 0, 0);
 
+        // --- queue space: ONE reservation per warp for the shadow rays of all lights (and, before the light loop, one for both
+        // child rays).  Every warp of the GPU hits the same two counters, so the atomics' round trips are long: they are issued as
+        // early as their counts are known and overlap the normal / texture / light work.  Per light the warp's rays stay
+        // contiguous: slot = base + (enabled-light index) * rays-per-light + rank.
+        const bool skip_mode = (F.debug_flags & 4u) != 0u;                       // opt-in zero-contribution skipping: per-light appends
+        const uint32_t lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
+        uint32_t sh_base = 0, sh_cnt = 0, sh_rank = 0;
+        {
+            bool rs = false;
+            if (hit) rs = S.mats[S.items[h.item].material].receive_shadow != 0u;
+            const uint32_t m = __ballot_sync(0xffffffffu, rs);
+            sh_cnt = __popc(m); sh_rank = __popc(m & lt_mask);
+            if (!skip_mode && lane == 0 && sh_cnt != 0u && n_enabled != 0u) sh_base = atomicAdd(out.shadow_count, sh_cnt * n_enabled);
+        }
         const uint32_t rng = F.monte_carlo ? mc_base(F.mc_seed, pixel, sample) : 0u;
         float3 view_dir = f3(0, 0, 1);
         if (hit) {
@@ -473,10 +489,17 @@ __global__ void __launch_bounds__(kShadeBlock, RTX_SHADE_MIN_BLOCKS) shade_kerne
             recv_shadow = mat.receive_shadow != 0; mat_mc = mat.monte_carlo != 0;
         }
 
-        // --- lights (:814-920): one warp-aggregated shadow-queue append per light ---
+        // --- queue space for both child rays: one reservation per warp, issued before the light loop (see the shadow reservation above)
+        uint32_t ch_base = 0;
+        const uint32_t m_refl = __ballot_sync(0xffffffffu, emit_refl), m_trans = __ballot_sync(0xffffffffu, emit_trans);
+        if (lane == 0 && (m_refl | m_trans) != 0u) ch_base = atomicAdd(out.child_count, __popc(m_refl) + __popc(m_trans));
+
+        // --- lights (:814-920) ---
+        uint32_t e_idx = 0;
         for (uint32_t li = 0; li < S.n_lights; li++) {
             const DLight& L = S.lights[li];
             if (!L.enabled) continue;                                             // uniform across the warp
+            if (e_idx == 0u && !skip_mode) sh_base = __shfl_sync(0xffffffffu, sh_base, 0);
             bool emit = false; float3 sdir = f3(0, 0, 1), c = f3(0, 0, 0); float len = 3.402823466e+38f;
             if (hit) {
                 const float3 lpos = f3(L.pos[0], L.pos[1], L.pos[2]), ldir = f3(L.dir[0], L.dir[1], L.dir[2]);
@@ -509,7 +532,8 @@ __global__ void __launch_bounds__(kShadeBlock, RTX_SHADE_MIN_BLOCKS) shade_kerne
                     if (F.monte_carlo && mat_mc) sdir = jitter(sdir, shadow_z_lo, rng, path, 2 + 2 * li);
                 } else direct = direct + c;
             }
-            const uint32_t slot = queue_append(out.shadow_count, emit);
+            const uint32_t slot = skip_mode ? queue_append(out.shadow_count, emit) : sh_base + e_idx * sh_cnt + sh_rank;
+            e_idx++;
             if (emit) {
                 if (slot < out.shadow_cap) {
                     const float3 so = xadd(hit_point, xscale(surface_normal, 0.001f));
@@ -525,8 +549,9 @@ __global__ void __launch_bounds__(kShadeBlock, RTX_SHADE_MIN_BLOCKS) shade_kerne
             if (acc.x != 0.0f || acc.y != 0.0f || acc.z != 0.0f) atomicAdd(&F.accum_c[pixel], make_float4(acc.x, acc.y, acc.z, 0.0f));
         }
         // --- child rays ---
+        ch_base = __shfl_sync(0xffffffffu, ch_base, 0);
         {
-            const uint32_t slot = queue_append(out.child_count, emit_refl);
+            const uint32_t slot = ch_base + __popc(m_refl & lt_mask);
             if (emit_refl) {
                 if (slot < out.child_cap) {
                     const float3 nd = xnormalize_s(refl_d);                         // :722-723 of the recursive call
@@ -537,7 +562,7 @@ __global__ void __launch_bounds__(kShadeBlock, RTX_SHADE_MIN_BLOCKS) shade_kerne
             }
         }
         {
-            const uint32_t slot = queue_append(out.child_count, emit_trans);
+            const uint32_t slot = ch_base + __popc(m_refl) + __popc(m_trans & lt_mask);
             if (emit_trans) {
                 if (slot < out.child_cap) {
                     const float3 nd = xnormalize_s(trans_d);
