@@ -508,7 +508,7 @@ __global__ void __launch_bounds__(kShadeBlock, RTX_SHADE_MIN_BLOCKS) shade_kerne
                 const float3 mi = -dtl;
                 const float3 reflect_dir = mi - (2.0f * dot3(surface_normal, mi)) * surface_normal;
                 const float spec_dot = fmaxf(dot3(reflect_dir, view_dir), 0.0f);
-                const float light_power = powf(spec_dot, shininess);
+                const float light_power = (spec_dot == 0.0f && shininess > 0.0f) ? 0.0f : powf(spec_dot, shininess);   // powf(+0, y > 0) = +0: skips ~40 instructions for every light behind the mirror direction
                 float intensity;
                 if (L.type == 0) intensity = L.intensity;
                 else {

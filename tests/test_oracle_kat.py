@@ -319,3 +319,16 @@ def test_author_rendering_of_the_sphere_room_pins_ball_semantics():
         r.set_options(ball_normal_outward_inside=outward)
         score[outward] = psnr(r.render(cam, cfg).image[..., :3].astype(np.float32), ref)
     assert score[0] >= 30.0 and score[0] >= score[1], score
+
+
+def test_u8_to_unit_float_shortcut_is_exact():
+    """The device converts texels with q = p*r; q += fma(-q, 255, p)*r (r = RN(1/255)) instead of an IEEE division
+    (csrc/rtx_device.cuh u8_unit): it must equal (float)p / 255.0f, the reference's and the oracle's expression
+    (shape/mod.rs:521-531 via image's to_rgba / 255.0), for every byte."""
+    f32 = np.float32
+    fma = lambda a, b, c: f32(np.float64(a) * np.float64(b) + np.float64(c))       # exact: 24+24-bit products fit a double
+    r = f32(1.0) / f32(255.0)
+    for p in range(256):
+        pf = f32(p)
+        q = f32(pf * r)
+        assert fma(fma(-q, f32(255.0), pf), r, q) == pf / f32(255.0), p
