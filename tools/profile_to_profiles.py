@@ -29,8 +29,8 @@ def val(r, key):
 traffic = collections.defaultdict(list)
 for r in rows[2:]:
     name = "closest_kernel" if "closest_kernel" in r[ix["Kernel Name"]] else "shadow_any_kernel" if "shadow_any" in r[ix["Kernel Name"]] else None
-    if name:
-        traffic[name].append(val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum"))
+    if name and float(r[ix["gpu__time_duration.sum"]].replace(",", "")) * {"ms": 1e3, "us": 1.0, "ns": 1e-3, "s": 1e6, "msecond": 1e3, "usecond": 1.0, "nsecond": 1e-3, "second": 1e6}.get(units[ix["gpu__time_duration.sum"]], 1.0) >= 50.0:
+        traffic[name].append(val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum"))          # tail waves of a few rays (< 50 us) are not representative
 out = {k: {"dram_bytes_per_launch": sum(v) / len(v), "launches_profiled": len(v), "source": "ncu --set full, profiles/%s_ncu_full_summary.txt" % tag} for k, v in traffic.items()}
 json.dump(out, open("profiles/r01_traffic.json", "w"), indent=1)
 print(json.dumps(out))
