@@ -82,6 +82,11 @@ def test_shard_pixel_counts_partition_the_frame():
         if w * h >= 64 * world:
             assert max(counts) - min(counts) <= tw * th * 2 + w * th                     # interleaving balances the ranks
     assert lib.rtx_shard_pixel_count(10, 10, C.byref(abi.RtxShard(3, 2, 8, 4))) == 0     # rank >= world
+    # the per-group rotation keeps a rank from owning fixed image columns (1280/8 = 160 tiles per row, 160 % 8 == 0: plain
+    # t % world would give rank 0 the tile columns 0, 8, 16, ... only — 8 % time imbalance on config 2)
+    px0 = shard_pixels(1280, 720, 0, 8, 8, 4)
+    cols = np.unique((px0 % 1280) // 8 % 8)
+    assert cols.size == 8
 
 
 def test_no_gpu_means_loud_failure_not_cpu_fallback():
