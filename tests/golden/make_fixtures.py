@@ -26,11 +26,15 @@ SCENES = {
     "kbert": (["scene/floor.json", "scene/kbert.json"], 1280, 720, 64, True),
     # glTF path (easy-gltf semantics: de-indexed mesh, file camera + KHR lights, PBR material with roughness jitter)
     "monkey_gltf": (["scene/models/monkey/monkey.gltf"], 1280, 720, 16, True),
+    # nested scene files (room.json + kbert.json through "type": "json" objects), three base-colour textures (png, gif), OBJ + MTL
+    "kbert_in_room": (["scene/kbert_in_room.json"], 1280, 720, 32, True),
 }
 
 
-def main(ref_root: str) -> None:
+def main(ref_root: str, only=None) -> None:
     for name, (files, w, h, samples, mc) in SCENES.items():
+        if only and name not in only:
+            continue
         sc = load_scene(files, w, h, asset_root=ref_root, samples=samples, monte_carlo=mc)
         fs = FlatScene.from_scene(sc)
         c = sc.config
@@ -44,4 +48,4 @@ def main(ref_root: str) -> None:
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else "/root/reference")
+    main(sys.argv[1] if len(sys.argv) > 1 else "/root/reference", only=sys.argv[2:] or None)   # [ref root] [fixture names...]

@@ -22,7 +22,7 @@ from tests.util import clone_cfg, lsb_stats, psnr, random_rays, scene_to_abi
 
 pytestmark = pytest.mark.gpu
 
-FIXTURES = ["c1_spheres", "c2_floor_monkey", "room_spheres", "kbert", "monkey_gltf"]
+FIXTURES = ["c1_spheres", "c2_floor_monkey", "room_spheres", "kbert", "monkey_gltf", "kbert_in_room"]
 
 
 def _pair(fs, w, h):
