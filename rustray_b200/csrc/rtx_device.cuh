@@ -697,7 +697,9 @@ __device__ __forceinline__ void lane_node(Lane& L, uint2* stack, const SceneDev&
     const uint32_t rel = __popc(imask & ~(0xFFFFFFFFu << slot));
     if (STATS) st.nodes++;
     // UT_ANY: the item level must see EVERY candidate (the order rule needs them), only BLAS nodes are clipped
-    const float tm = (MODE == UT_ANY && L.blas_base < 0) ? 3.402823466e+38f : L.tmax;
+    // ... until an occluder is known: after that only candidates that sort BEFORE it matter (key < occluder's key), and an
+    // item's key is never smaller than the distance at which the ray enters its world box
+    const float tm = (MODE == UT_ANY && L.blas_base < 0) ? (L.bflags != 0u ? L.bkey : 3.402823466e+38f) : L.tmax;
     node_test(S.nodes, base + rel, L.r, 0.0f, tm, L.ng, L.tg);
 }
 
@@ -708,10 +710,13 @@ __device__ __forceinline__ void lane_note_other(Lane& L, float key, uint32_t ite
     const float ok = __uint_as_float(L.bprim);
     if (L.bface == 0xFFFFFFFFu || key < ok || (key == ok && item < L.bface)) { L.bprim = __float_as_uint(key); L.bface = item; }
 }
-__device__ __forceinline__ void lane_any_hit(Lane& L, float key, uint32_t item) {
+__device__ __forceinline__ void lane_any_hit(Lane& L, float key, uint32_t item, const SceneDev& S) {
     L.bitem = item; L.bkey = key; L.bflags = 1u;                          // bflags = 1: enumeration mode (no more BLAS work)
     if (L.blas_base >= 0) { L.sp = L.blas_base; L.blas_base = -1; L.r = L.w; }
     L.ng = make_uint2(0u, 0u); L.tg = make_uint2(0u, 0u);
+    // directional light (no finite light distance) and no alpha-textured occluder anywhere: the first-hit order cannot change
+    // "occluded" any more (see shadow_any_kernel), the other candidates need not be enumerated
+    if (!S.any_alpha_tex && L.tmax >= 3.402823466e+38f) L.sp = 0;
 }
 
 // WHICH: 0 = whatever the entry is; 1 = the caller knows it is a triangle (L.blas_base >= 0); 2 = an item of the TLAS.
@@ -730,7 +735,7 @@ __device__ __forceinline__ void lane_leaf(Lane& L, uint2* stack, const SceneDev&
         float toi; uint32_t back;
         if (tri_cast(f3(v0.x, v0.y, v0.z), f3(v1.x, v1.y, v1.z), f3(v2.x, v2.y, v2.z), L.r.o, L.r.d, toi, back)) {
             if (MODE == UT_CLOSEST) lane_accept(L, toi, L.cur_key, L.cur_item, prim, __float_as_uint(v0.w), back);
-            else if (toi <= L.tmax) lane_any_hit(L, L.cur_key, L.cur_item);
+            else if (toi <= L.tmax) lane_any_hit(L, L.cur_key, L.cur_item, S);
         }
         return;
     }
@@ -768,7 +773,7 @@ __device__ __forceinline__ void lane_leaf(Lane& L, uint2* stack, const SceneDev&
         if (STATS) n_sph++;
         const bool h = ball_cast(lo.w, lo3, ld3, solid, t, inside);
         if (MODE == UT_CLOSEST) { if (h) lane_accept(L, t, key, ii, 0u, 0u, inside ? HF_INSIDE : 0u); }
-        else if (h && t <= L.tmax) lane_any_hit(L, key, ii);
+        else if (h && t <= L.tmax) lane_any_hit(L, key, ii, S);
         else lane_note_other(L, key, ii);
         return;
     }
