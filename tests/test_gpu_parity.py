@@ -366,6 +366,22 @@ def test_progressive_snapshots_of_a_frame_in_flight():
     assert g2.is_done() and np.array_equal(g2.frame.objects, want2)
 
 
+@pytest.mark.parametrize("w,h,samples", [(37, 23, 33), (129, 65, 2), (64, 36, 200), (250, 141, 7), (33, 9, 1000)])
+def test_odd_frame_sizes_and_sample_counts(w, h, samples):
+    """Ragged tiles and sample counts that are not multiples of the 32-sample ray groups / fill a batch unevenly: the
+    deterministic anti-aliased frame must trace exactly the oracle's rays and give its ids, depths and (1 LSB) colours."""
+    fs, cam, cfg = abi.load_fixture("kbert", samples=samples, monte_carlo=0)
+    cam = abi.resize_camera(cam, w, h)
+    g, c = _pair(fs, w, h)
+    fg, fc = g.start(cam, cfg), c.render(cam, cfg)
+    assert fg.stats.primary_samples == w * h * samples
+    for a, b in ((fg.stats.rays_closest, fc.stats.rays_closest), (fg.stats.rays_shadow, fc.stats.rays_shadow)):
+        assert abs(int(a) - int(b)) <= 1e-4 * b + 1
+    assert np.array_equal(fg.objects, fc.objects)
+    assert np.allclose(fg.depth, fc.depth, rtol=1e-5, atol=1e-6)
+    assert lsb_stats(fg.image, fc.image)[0] >= 0.999
+
+
 def test_error_codes_instead_of_panics():
     fs, cam, cfg = abi.load_fixture("c1_spheres")
     g = RendererManager(16, 16, fs)
