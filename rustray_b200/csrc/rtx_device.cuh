@@ -696,10 +696,13 @@ __device__ __forceinline__ void lane_node(Lane& L, uint2* stack, const SceneDev&
     const uint32_t slot = (cbit - 24u) ^ (L.r.octinv4 & 0xffu);
     const uint32_t rel = __popc(imask & ~(0xFFFFFFFFu << slot));
     if (STATS) st.nodes++;
-    // UT_ANY: the item level must see EVERY candidate (the order rule needs them), only BLAS nodes are clipped
+    // UT_ANY: the item level must see every candidate that can matter to the order rule
     // ... until an occluder is known: after that only candidates that sort BEFORE it matter (key < occluder's key), and an
     // item's key is never smaller than the distance at which the ray enters its world box
-    const float tm = (MODE == UT_ANY && L.blas_base < 0) ? (L.bflags != 0u ? L.bkey : 3.402823466e+38f) : L.tmax;
+    // Before an occluder is known the walk is clipped at the light distance: an item the ray enters beyond the light can neither
+    // occlude nor sort before an occluder whose own key is <= the light distance (an occluder with a larger key — the ray
+    // starts inside its non-solid box — sends the ray to the exact walk, see shadow_any_kernel).
+    const float tm = (MODE == UT_ANY && L.blas_base < 0) ? (L.bflags != 0u ? L.bkey : L.tmax) : L.tmax;
     node_test(S.nodes, base + rel, L.r, 0.0f, tm, L.ng, L.tg);
 }
 

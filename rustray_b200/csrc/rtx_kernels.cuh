@@ -222,7 +222,10 @@ __global__ void __launch_bounds__(kTraceBlock, RTX_MIN_BLOCKS) shadow_any_kernel
                 const bool occluded = L.bitem != 0xFFFFFFFFu;
                 const float okey = __uint_as_float(L.bprim);
                 const bool earlier_other = L.bface != 0xFFFFFFFFu && (okey < L.bkey || (okey == L.bkey && L.bface < L.bitem));
-                if (!occluded || (!S.any_alpha_tex && (L.tmax >= 3.402823466e+38f || !earlier_other))) {
+                // final unless the reference's first-hit order could change the answer: an alpha-textured material exists, or (finite
+                // light distance and) another candidate sorts before the occluder, or the occluder's own key lies beyond the light
+                // (then the clipped item walk may not have seen every earlier candidate)
+                if (!occluded || (!S.any_alpha_tex && (L.tmax >= 3.402823466e+38f || (!earlier_other && !(L.bkey > L.tmax))))) {
                     const float4 rc = q.c[my];
                     const float k = occluded ? 1.0f - rc.w : 1.0f;               // raytracing.rs:898,912
                     atomicAdd(&F.accum_c[__float_as_uint(q.d[my].w)], make_float4(rc.x * k, rc.y * k, rc.z * k, 0.0f));
