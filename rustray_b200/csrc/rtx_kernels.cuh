@@ -463,7 +463,6 @@ __global__ void __launch_bounds__(kShadeBlock, RTX_SHADE_MIN_BLOCKS) shade_kerne
             float alpha = mat.alpha * base_color.w;                                // :806-811
             if ((tex_mask >> 4) & 1u) alpha *= texc[4].x;
 
-            const float kr = fresnel(d, surface_normal, mat.refraction_index);   // :925
             float reflectivity = mat.reflectivity;                                // :928-933
             if ((tex_mask >> 7) & 1u) reflectivity = texc[7].x;
             const bool can_recurse = depth <= F.max_recursion;
@@ -472,7 +471,11 @@ __global__ void __launch_bounds__(kShadeBlock, RTX_SHADE_MIN_BLOCKS) shade_kerne
             if (alpha < 1.0f && can_recurse)                                      // :948-952
                 trans_exists = create_transmission(surface_normal, d, hit_point, mat.refraction_index, trans_o, trans_d);
             const float a = trans_exists ? alpha : ((alpha < 1.0f && !can_recurse) ? alpha : 1.0f);   // :959-975 (TIR keeps 1)
-            const float kt = trans_exists ? ((kr < 1.0f ? (1.0f - kr) : 1.0f) * (1.0f - alpha)) : 0.0f;
+            float kt = 0.0f;
+            if (trans_exists) {                                                   // kr (:925) only matters when a transmission ray exists
+                const float kr = fresnel(d, surface_normal, mat.refraction_index);
+                kt = (kr < 1.0f ? (1.0f - kr) : 1.0f) * (1.0f - alpha);
+            }
             const float fog = fminf(F.fog_density * hit_dist, 1.0f);              // :978-982
             float ao = 1.0f;
             if ((tex_mask >> 6) & 1u) ao = texc[6].x;                                  // :985-991
