@@ -125,9 +125,11 @@ __device__ __forceinline__ float3 xnormalize(float3 a) { float n = xnorm(a); ret
 #define RTX_XNORM_NOINLINE 1
 #endif
 #if RTX_XNORM_NOINLINE
-__device__ __noinline__ float3 xnormalize_s(float3 a) { float n = xnorm(a); return f3(xd(a.x, n), xd(a.y, n), xd(a.z, n)); }
+__device__ __noinline__ float4 xnormalize_len_s(float3 a) { float n = xnorm(a); return make_float4(xd(a.x, n), xd(a.y, n), xd(a.z, n), n); }   // .w = the norm
+__device__ __forceinline__ float3 xnormalize_s(float3 a) { const float4 r = xnormalize_len_s(a); return f3(r.x, r.y, r.z); }
 #else
 __device__ __forceinline__ float3 xnormalize_s(float3 a) { return xnormalize(a); }
+__device__ __forceinline__ float4 xnormalize_len_s(float3 a) { float n = xnorm(a); return make_float4(xd(a.x, n), xd(a.y, n), xd(a.z, n), n); }
 #endif
 // row r of an affine 3x4 (row = m[r][0..3]) times (x,y,z,w): ((m0*x + m1*y) + m2*z) + m3*w
 __device__ __forceinline__ float xrow(float4 r, float3 v, float w) { return xa(xa(xa(xm(r.x, v.x), xm(r.y, v.y)), xm(r.z, v.z)), xm(r.w, w)); }

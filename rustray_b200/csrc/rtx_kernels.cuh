@@ -509,7 +509,8 @@ __global__ void __launch_bounds__(kShadeBlock, RTX_SHADE_MIN_BLOCKS) shade_kerne
             bool emit = false; float3 sdir = f3(0, 0, 1), c = f3(0, 0, 0); float len = 3.402823466e+38f;
             if (hit) {
                 const float3 lpos = f3(L.pos[0], L.pos[1], L.pos[2]), ldir = f3(L.dir[0], L.dir[1], L.dir[2]);
-                const float3 dtl = L.type == 0 ? xnormalize_s(xneg(ldir)) : xnormalize_s(xsub(lpos, hit_point));
+                const float4 dtl4 = xnormalize_len_s(L.type == 0 ? xneg(ldir) : xsub(lpos, hit_point));   // .w = |lpos - hit_point| for point / spot lights
+                const float3 dtl = f3(dtl4.x, dtl4.y, dtl4.z);
                 const float dot_light = fmaxf(dot3(surface_normal, dtl), 0.0f);
                 const float3 mi = -dtl;
                 const float3 reflect_dir = mi - (2.0f * dot3(surface_normal, mi)) * surface_normal;
@@ -518,7 +519,7 @@ __global__ void __launch_bounds__(kShadeBlock, RTX_SHADE_MIN_BLOCKS) shade_kerne
                 float intensity;
                 if (L.type == 0) intensity = L.intensity;
                 else {
-                    const float r2 = xnorm(xsub(lpos, hit_point));
+                    const float r2 = dtl4.w;                                      // the same xnorm(xsub(lpos, hit_point)), computed once
                     intensity = L.intensity / (4.0f * PI * r2);
                     len = r2;
                     if (L.type == 2) {
