@@ -1,0 +1,47 @@
+"""CPU suite: bench.py's JSON-line contract.  The reference arm (`--impl reference`: the CPU oracle on the host cores) runs
+for real on a bounded sample; the GPU arm's line is checked on the committed result of the last B200 run."""
+import glob
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+             "data", "config", "e2e", "gpu_launches"}
+
+
+def test_reference_arm_prints_one_contract_line():
+    r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "0"], cwd=ROOT, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and BASE_KEYS <= set(d) and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["metric"].startswith("Mrays/s") and d["unit"] == "Mrays/s" and d["vs_baseline"] is None and d["scaling"] == "weak"
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "2x2 cell" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "configs[1]" in d["config"]["workload"]
+
+
+def test_reference_arm_other_ranks_stay_silent():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"], cwd=ROOT,
+                       capture_output=True, text=True, timeout=120, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_committed_gpu_line_has_the_contract_keys():
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_v*_bench.json")))
+    assert files
+    d = json.load(open(files[-1]))
+    assert BASE_KEYS | {"clocks", "roofline", "cpu_baseline"} <= set(d)
+    assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["dtype"] == "f32" and d["gpu_launches"] > 0
+    rf = d["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(rf) and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-6
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] == 1280 * 720 * 24 + d["e2e"]["d2h_bytes_per_step"] % (1280 * 720 * 24)
+    assert d["e2e"]["value"] <= d["value"] * 1.001                  # host copies are inside the timed region
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
