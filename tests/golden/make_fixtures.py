@@ -28,6 +28,8 @@ SCENES = {
     "monkey_gltf": (["scene/models/monkey/monkey.gltf"], 1280, 720, 16, True),
     # nested scene files (room.json + kbert.json through "type": "json" objects), three base-colour textures (png, gif), OBJ + MTL
     "kbert_in_room": (["scene/kbert_in_room.json"], 1280, 720, 32, True),
+    # a sphere with base, specular and normal maps (sphere uv + tangent frame, three 2048x1024 JPEGs) in the textured room
+    "earth_in_room": (["scene/earth_in_room.json"], 1280, 720, 16, True),
 }
 
 
