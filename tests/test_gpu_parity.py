@@ -22,7 +22,8 @@ from tests.util import clone_cfg, lsb_stats, psnr, random_rays, scene_to_abi
 
 pytestmark = pytest.mark.gpu
 
-FIXTURES = ["c1_spheres", "c2_floor_monkey", "room_spheres", "kbert", "monkey_gltf", "kbert_in_room"]
+UV_FEEDS_GEOMETRY = {"earth_in_room"}
+FIXTURES = ["c1_spheres", "c2_floor_monkey", "room_spheres", "kbert", "monkey_gltf", "kbert_in_room", "earth_in_room"]
 
 
 def _pair(fs, w, h):
@@ -79,7 +80,13 @@ def test_deterministic_image_parity(name):
     assert np.array_equal(fg.depth, fc.depth)                                                       # primary hit distances bit-equal
     hit = fc.objects != 0
     assert np.isnan(fg.normals[~hit]).all() and np.allclose(fg.normals[hit], fc.normals[hit], rtol=1e-4, atol=1e-6)
-    assert (fg.stats.rays_closest, fg.stats.rays_shadow) == (fc.stats.rays_closest, fc.stats.rays_shadow)
+    if name in UV_FEEDS_GEOMETRY:
+        # a normal-mapped SPHERE: its uv goes through atan2f / acosf (glibc vs CUDA differ in the last ulps), the normal map turns
+        # that into reflection-ray geometry, and a grazing ray deep in the tree may fall on the other side of an edge
+        for a, b in ((fg.stats.rays_closest, fc.stats.rays_closest), (fg.stats.rays_shadow, fc.stats.rays_shadow)):
+            assert abs(int(a) - int(b)) <= 1e-5 * b + 1
+    else:
+        assert (fg.stats.rays_closest, fg.stats.rays_shadow) == (fc.stats.rays_closest, fc.stats.rays_shadow)
     assert fg.stats.primary_samples == 400 * 225 and fg.stats.kernel_launches > 0
 
 
