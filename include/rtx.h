@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RTX_ABI_VERSION 1
+#define RTX_ABI_VERSION 2
 
 /* error codes */
 #define RTX_OK              0
@@ -39,7 +39,8 @@ extern "C" {
                                    Vector3::from_homogeneous, src/shape/mod.rs:760)          */
 #define RTX_E_EMPTY_MESH   -5   /* mesh with 0 triangles (parry TriMesh::new panics)         */
 #define RTX_E_CANCELLED    -6   /* rtx_render_stop was called while the frame was in flight  */
-#define RTX_E_BUSY         -7   /* a frame is already in flight on this scene handle         */
+#define RTX_E_BUSY         -7   /* a frame is in flight on this scene handle (frames, item / light updates; probes are
+                                   always allowed: they use their own stream and buffers)     */
 
 /* TextureType order — reference src/shape/mod.rs:633-643 */
 enum {
@@ -175,6 +176,8 @@ typedef struct RtxStats {
     float shade_ms;        /* device_ms - closest_ms - shadow_ms (raygen, shade, resolve, gaps)     */
     uint64_t h2d_bytes, d2h_bytes;
     uint64_t rays_shadow_skipped;   /* RTX_OPT_SKIP_ZERO_SHADOW: shadow rays not traced (included in rays_shadow) */
+    uint32_t host_syncs;            /* stream synchronisations inside the frame: 1 for a sync-free frame, waves + 1 otherwise */
+    uint32_t reserved;
 } RtxStats;
 
 typedef struct RtxRay { float origin[3]; float dir[3]; } RtxRay;
@@ -188,6 +191,19 @@ typedef struct RtxHit {
     uint32_t reserved;
 } RtxHit;
 
+/* One shadow query answered by the PRODUCTION shadow kernels (any-hit + reference-order walk), i.e. the outcome of
+ * `trace(&shadow_ray, true, true, depth)` followed by the light-distance test and the attenuation of
+ * reference src/raytracing.rs:883-914 for a unit light contribution:
+ *   k              1 when lit, else 1 - receiver.alpha [* occluder alpha-texture texel at the receiver's uv (sic, :905)]
+ *   lit            1 = no item hit at all, or the first item hit (bbox-key order) is hit beyond the light distance
+ *   occluder_index an item with a hit at toi <= light distance (-1 when lit).  It is the reference's first-hit item
+ *                  whenever the order rule can matter (alpha-textured occluder, or a finite light distance with several
+ *                  candidates); otherwise any occluder
+ *   t, face_id     hit distance / parry face id on the occluder, only when its material has an alpha texture (else -1, 0) */
+typedef struct RtxShadowHit {
+    float k; int32_t lit; int32_t occluder_index; float t; uint32_t face_id; uint32_t reserved[3];
+} RtxShadowHit;
+
 typedef struct RtxBvhInfo {
     uint32_t n_nodes, n_triangles, n_items, tlas_nodes;
     uint64_t node_bytes, triangle_bytes, item_bytes, texture_bytes;
@@ -200,6 +216,15 @@ typedef struct RtxScene RtxScene;   /* opaque */
  * description, builds the per-mesh wide BVHs and the item-level structure, uploads to
  * `device` (CUDA ordinal).  Fails with RTX_E_NO_DEVICE when there is no GPU. */
 int rtx_scene_create(const RtxSceneDesc* desc, int device, RtxScene** out);
+
+/* Same scene on several GPUs of ONE process — the reference has one RendererManager::start per frame
+ * (src/renderer.rs:105-172), so a host that owns that call cannot be one process per GPU.  The scene is built once on
+ * devices[0] and copied device-to-device to the others; rtx_render_frame / _async / _device (shard = NULL) then split
+ * the frame into interleaved tiles, one host thread and one stream per device, and every device's resolve kernel stores
+ * its finished pixels directly into the frame buffers on devices[0] through NVLink peer memory (no separate gather).
+ * Needs peer access between devices[0] and every other listed device.  All other calls take the handle unchanged. */
+int rtx_scene_create_multi(const RtxSceneDesc* desc, const int* devices, uint32_t n_devices, RtxScene** out);
+int rtx_scene_device_count(const RtxScene* scene);
 
 /* Scene::apply_frame / ShapeBasics::apply_mat + Scene::update (reference src/scene.rs:1695-1713,
  * src/shape/mod.rs:748-753,1674-1688): replace transforms of n items (by position in items). */
@@ -255,11 +280,36 @@ int rtx_shard_unpack(uint32_t width, uint32_t height, const RtxShard* shard,
                      const void* d_packed, void* d_rgba, void* d_normals, void* d_depth,
                      void* d_object_ids, void* cuda_stream);
 
+/* Rank 0 after ONE gather into a contiguous buffer (rank r's packed shard at d_packed_all + r * stride_bytes): scatter
+ * the shards of ranks first_rank .. world-1 into the frame buffers with one kernel. */
+int rtx_shard_unpack_all(uint32_t width, uint32_t height, uint32_t world, uint32_t tile_w, uint32_t tile_h,
+                         uint32_t first_rank, const void* d_packed_all, uint64_t stride_bytes,
+                         void* d_rgba, void* d_normals, void* d_depth, void* d_object_ids, void* cuda_stream);
+
+/* Frame buffers that OTHER PROCESSES render into (one process per GPU under torchrun): 24 bytes per pixel in one
+ * device allocation, rgba8[n] | normals f32[3n] | depth f32[n] | ids u32[n] (= the four buffers of Run, src/run.rs:117-120).
+ * The owner exports a 64-byte CUDA IPC handle, the other ranks open it and pass rtx_gbuffer_pointers() as the outputs of
+ * rtx_render_frame_device with their shard: finished pixels travel as NVLink stores from the resolve kernel, and after a
+ * barrier the owner holds the whole frame.  rtx_gbuffer_download copies it to (page-locked) host memory. */
+typedef struct RtxGBuffer RtxGBuffer;
+int rtx_gbuffer_create(int device, uint32_t width, uint32_t height, RtxGBuffer** out);
+int rtx_gbuffer_export(RtxGBuffer* g, uint8_t handle[64]);
+int rtx_gbuffer_open(int device, uint32_t width, uint32_t height, const uint8_t handle[64], RtxGBuffer** out);
+int rtx_gbuffer_pointers(const RtxGBuffer* g, void** d_rgba, void** d_normals, void** d_depth, void** d_object_ids);
+int rtx_gbuffer_download(const RtxGBuffer* g, uint8_t* rgba, float* normals, float* depth, uint32_t* object_ids, void* cuda_stream);
+int rtx_gbuffer_destroy(RtxGBuffer* g);
+
 /* Raytracing::trace (reference src/raytracing.rs:429-490) and, with for_shadow = 0 on a
  * primary ray, Raytracing::pick (:237-273).  HOST arrays of n rays / n hits.  Ray directions
  * are used as given (the callers in the reference normalise first, :262,:723). */
 int rtx_trace_probe(RtxScene* scene, const RtxRay* rays, size_t n, int for_shadow,
                     int stop_on_first_hit, uint32_t depth, RtxHit* hits);
+
+/* Shadow rays through the production kernels (see RtxShadowHit).  light_distance: n floats, NULL = +inf for every ray
+ * (directional light, raytracing.rs:887); receiver_item: index of the item the shadow ray leaves from (its material's alpha
+ * and its get_uv enter the attenuation, :897,:905), NULL = alpha 1 / item 0. */
+int rtx_shadow_probe(RtxScene* scene, const RtxRay* rays, const float* light_distance, const int32_t* receiver_item,
+                     size_t n, uint32_t depth, RtxShadowHit* out);
 
 /* The per-pixel sample sub-grid of Raytracing::render (reference src/raytracing.rs:290-313):
  * cell_size, and `samples` (x_i, y_i) pairs after StdRng::seed_from_u64(0) shuffle + truncate.
@@ -271,6 +321,10 @@ int rtx_scene_destroy(RtxScene* scene);
 const char* rtx_last_error(void);
 int rtx_abi_version(void);
 int rtx_device_count(void);
+
+/* Read bandwidth of a `bytes`-sized buffer swept `iters` times with 128-bit loads (ld.global.cg): with bytes well below
+ * the 126 MB L2 this is the L2 figure SURVEY.md §8(d) asks to quote next to the HBM roofline for L2-resident scenes. */
+int rtx_bandwidth_probe(int device, uint64_t bytes, uint32_t iters, float* gbytes_per_s);
 
 /* Post-processing on the finished G-buffer (reference src/post_processing.rs:77-181), device
  * side, in place on d_rgba.  cavity/outline as in PostProcessingConfig. */

@@ -190,6 +190,8 @@ struct Scene {
     std::vector<Tex> texs; std::vector<RtxLight> lights;
     bool ball_normal_flip_inside = true;
     bool brute_force = false;
+    // item BVH used above BVH_MIN_ITEMS items (Scene::update, scene.rs:1681-1687; world boxes as shape/mod.rs:48-79)
+    std::vector<Bvh2Node> item_nodes; std::vector<uint32_t> item_order;
 };
 struct Ray { V3 o, d; };
 struct Counters { uint64_t closest = 0, shadow = 0; };
@@ -425,14 +427,87 @@ bool item_intersect(const Scene& sc, const Item& it, const Ray& r, bool force_no
 // ------------------------------------------------------------------------------------------
 struct Hit { float t; V3 n; int item; uint32_t face; };
 
-// Raytracing::trace (raytracing.rs:429-490).  items.len() > BVH_MIN_ITEMS uses the bvh crate as a
-// conservative candidate filter; restated as "all items in scene order" (§8(c): acceptable).
+// Scene::update's item BVH (scene.rs:1681-1687, bvh crate 0.7 BVHNode::build over the Bounded impl of shape/mod.rs:48-79:
+// the eight corners of the local box through `trans`).  Only a candidate filter: boxes are padded so that no item that
+// passes the exact local-space slab test (intersect_b_box) is ever dropped, and candidates are handed out in scene order,
+// so trace() returns exactly what the all-items loop returns — the crate's DFS order (ties between equal bbox
+// distances only) is not reproduced.  Median split on the widest centroid axis, <= 2 items per leaf.
+constexpr size_t BVH_MIN_ITEMS = 50;                                       // raytracing.rs:23
+void build_item_bvh(Scene& sc) {
+    sc.item_nodes.clear(); sc.item_order.clear();
+    const size_t n = sc.items.size();
+    if (n <= BVH_MIN_ITEMS) return;
+    std::vector<float> lo(3 * n), hi(3 * n), ce(3 * n);
+    for (size_t i = 0; i < n; i++) {
+        const Item& it = sc.items[i];
+        float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int c = 0; c < 8; c++) {
+            V3 p = {(c & 1) ? it.hi.x : it.lo.x, (c & 2) ? it.hi.y : it.lo.y, (c & 4) ? it.hi.z : it.lo.z};
+            float o[4]; mul4(it.trans, p.x, p.y, p.z, 1.0f, o);
+            for (int k = 0; k < 3; k++) { mn[k] = rmin(mn[k], o[k]); mx[k] = rmax(mx[k], o[k]); }
+        }
+        for (int k = 0; k < 3; k++) {
+            float pad = 1e-4f * (std::fabs(mn[k]) + std::fabs(mx[k])) + 1e-5f;
+            lo[3 * i + k] = mn[k] - pad; hi[3 * i + k] = mx[k] + pad; ce[3 * i + k] = 0.5f * (mn[k] + mx[k]);
+        }
+    }
+    sc.item_order.resize(n);
+    for (size_t i = 0; i < n; i++) sc.item_order[i] = (uint32_t)i;
+    struct Job { uint32_t node, first, count; };
+    std::vector<Job> jobs; sc.item_nodes.push_back({}); jobs.push_back({0, 0, (uint32_t)n});
+    while (!jobs.empty()) {
+        Job j = jobs.back(); jobs.pop_back();
+        Bvh2Node nd; for (int k = 0; k < 3; k++) { nd.lo[k] = INFINITY; nd.hi[k] = -INFINITY; }
+        float cl[3] = {INFINITY, INFINITY, INFINITY}, ch[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (uint32_t q = j.first; q < j.first + j.count; q++) {
+            uint32_t i = sc.item_order[q];
+            for (int k = 0; k < 3; k++) { nd.lo[k] = rmin(nd.lo[k], lo[3 * i + k]); nd.hi[k] = rmax(nd.hi[k], hi[3 * i + k]); cl[k] = rmin(cl[k], ce[3 * i + k]); ch[k] = rmax(ch[k], ce[3 * i + k]); }
+        }
+        int ax = 0; for (int k = 1; k < 3; k++) if (ch[k] - cl[k] > ch[ax] - cl[ax]) ax = k;
+        if (j.count <= 2 || !(ch[ax] > cl[ax])) { nd.left = j.first; nd.count = j.count; sc.item_nodes[j.node] = nd; continue; }
+        uint32_t mid = j.first + j.count / 2;
+        std::nth_element(sc.item_order.begin() + j.first, sc.item_order.begin() + mid, sc.item_order.begin() + j.first + j.count,
+                         [&](uint32_t a, uint32_t b) { return ce[3 * a + ax] < ce[3 * b + ax]; });
+        nd.left = (uint32_t)sc.item_nodes.size(); nd.count = 0;
+        sc.item_nodes[j.node] = nd;
+        sc.item_nodes.push_back({}); sc.item_nodes.push_back({});
+        jobs.push_back({nd.left, j.first, mid - j.first}); jobs.push_back({nd.left + 1, mid, j.first + j.count - mid});
+    }
+}
+// Scene::get_possible_hits_by_ray (scene.rs:1715-1722): candidate items, returned in scene order
+inline void item_bvh_candidates(const Scene& sc, const Ray& r, std::vector<uint32_t>& out) {
+    out.clear();
+    const float o[3] = {r.o.x, r.o.y, r.o.z}, d[3] = {r.d.x, r.d.y, r.d.z};
+    uint32_t stack[64]; int sp = 0; stack[sp++] = 0;
+    while (sp) {
+        const Bvh2Node& n = sc.item_nodes[stack[--sp]];
+        float t0 = 0.0f, t1 = std::numeric_limits<float>::max(); bool miss = false;
+        for (int k = 0; k < 3 && !miss; k++) {
+            if (d[k] == 0.0f) { if (o[k] < n.lo[k] || o[k] > n.hi[k]) miss = true; continue; }
+            float inv = 1.0f / d[k], a = (n.lo[k] - o[k]) * inv, b = (n.hi[k] - o[k]) * inv;
+            if (a > b) std::swap(a, b);
+            t0 = rmax(t0, a); t1 = rmin(t1, b);
+            if (t0 > t1 * 1.00001f + 1e-6f) miss = true;
+        }
+        if (miss) continue;
+        if (n.count) { for (uint32_t q = 0; q < n.count; q++) out.push_back(sc.item_order[n.left + q]); }
+        else if (sp + 2 <= 64) { stack[sp++] = n.left; stack[sp++] = n.left + 1; }
+    }
+    std::sort(out.begin(), out.end());
+}
+
+// Raytracing::trace (raytracing.rs:429-490).  items.len() > BVH_MIN_ITEMS takes its candidates from the item BVH.
 bool trace(const Scene& sc, const Ray& r, bool stop_on_first_hit, bool for_shadow, uint32_t depth, Hit* out, Counters* cnt) {
     if (cnt) { if (for_shadow) cnt->shadow++; else cnt->closest++; }
     struct Cand { int item; float dist; };
     Cand small[64]; std::vector<Cand> big; Cand* hits = small; size_t nh = 0;
-    if (sc.items.size() > 64) { big.resize(sc.items.size()); hits = big.data(); }
-    for (size_t i = 0; i < sc.items.size(); i++) {
+    const bool use_bvh = !sc.item_nodes.empty() && !sc.brute_force;
+    static thread_local std::vector<uint32_t> cand;
+    if (use_bvh) item_bvh_candidates(sc, r, cand);
+    const size_t n_cand = use_bvh ? cand.size() : sc.items.size();
+    if (n_cand > 64) { big.resize(n_cand); hits = big.data(); }
+    for (size_t q = 0; q < n_cand; q++) {
+        const size_t i = use_bvh ? cand[q] : q;
         const Item& it = sc.items[i];
         float dist;
         if (intersect_b_box(it, r, for_shadow, &dist)) {
@@ -784,8 +859,16 @@ int oracle_scene_create(const RtxSceneDesc* d, int /*device*/, RtxScene** out) {
         for (uint32_t k = 0; k < s.n_normals; k++) m.normals.push_back({s.normals[3 * k], s.normals[3 * k + 1], s.normals[3 * k + 2]});
         if (s.n_normal_faces) m.n_idx.assign(s.normals_indices, s.normals_indices + 3 * (size_t)s.n_normal_faces);
         for (uint32_t v : m.idx) if (v >= s.n_vertices) { delete sc; g_err = "index out of range"; return RTX_E_INVALID; }
-        build_bvh2(m);
         sc->meshes.push_back(std::move(m));
+    }
+    {   // oracle-side acceleration structures, one thread per mesh (config 5: 64 meshes of 156 k triangles)
+        std::atomic<size_t> next{0};
+        auto work = [&]() { for (size_t i = next.fetch_add(1); i < sc->meshes.size(); i = next.fetch_add(1)) build_bvh2(sc->meshes[i]); };
+        std::vector<std::thread> th;
+        const unsigned nt = std::max(1u, std::min<unsigned>((unsigned)sc->meshes.size(), std::thread::hardware_concurrency()));
+        for (unsigned t = 1; t < nt; t++) th.emplace_back(work);
+        work();
+        for (auto& t : th) t.join();
     }
     for (uint32_t i = 0; i < d->n_items; i++) {
         Item it; it.d = d->items[i];
@@ -796,6 +879,7 @@ int oracle_scene_create(const RtxSceneDesc* d, int /*device*/, RtxScene** out) {
         sc->items.push_back(it);
     }
     sc->lights.assign(d->lights, d->lights + d->n_lights);
+    build_item_bvh(*sc);
     *out = reinterpret_cast<RtxScene*>(sc);
     return RTX_OK;
 }
@@ -810,6 +894,7 @@ int oracle_scene_update_items(RtxScene* s, const RtxItemXform* x, size_t n) {
         memcpy(it.d.trans, x[i].trans, 64); memcpy(it.d.tran_inverse, x[i].tran_inverse, 64);
         update_item(*sc, it);
     }
+    build_item_bvh(*sc);                                                  // Scene::update rebuilds it on every start (scene.rs:1674-1688)
     return RTX_OK;
 }
 
@@ -847,6 +932,40 @@ int oracle_trace_probe(RtxScene* s, const RtxRay* rays, size_t n, int for_shadow
                 o.item_id = sc.items[h.item].d.id; o.face_id = h.face; o.item_index = h.item;
             } else { o.t = -1.0f; o.item_index = -1; }
             hits[i] = o;
+        }
+    });
+    for (auto& t : th) t.join();
+    return RTX_OK;
+}
+
+// The shadow query of the shading loop (raytracing.rs:872-914) for a unit light contribution — the CPU statement of what
+// rtx_shadow_probe reads back from the production shadow kernels.  occluder_index / t / face_id are ALWAYS the reference's
+// first-hit item here (the device reports t / face only for alpha-textured occluders).
+int oracle_shadow_probe(RtxScene* s, const RtxRay* rays, const float* light_distance, const int32_t* receiver_item, size_t n, uint32_t depth,
+                        RtxShadowHit* out) {
+    const Scene& sc = *reinterpret_cast<Scene*>(s);
+    unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++) th.emplace_back([&, t]() {
+        for (size_t i = t; i < n; i += nt) {
+            Ray r{{rays[i].origin[0], rays[i].origin[1], rays[i].origin[2]}, {rays[i].dir[0], rays[i].dir[1], rays[i].dir[2]}};
+            RtxShadowHit o; memset(&o, 0, sizeof(o));
+            Hit sh; bool shit = trace(sc, r, true, true, depth, &sh, nullptr);                  // :883
+            bool in_light = !shit;
+            if (!in_light && light_distance) in_light = sh.t > light_distance[i];              // :885-892 (point / spot lights only)
+            o.lit = in_light ? 1 : 0; o.k = 1.0f; o.occluder_index = -1; o.t = -1.0f;
+            if (!in_light) {                                                                   // :895-913
+                const int recv = receiver_item ? receiver_item[i] : -1;
+                const Item& item = sc.items[recv >= 0 ? recv : 0];
+                float shadow_source_alpha = recv >= 0 ? sc.mats[item.d.material].alpha : 1.0f;
+                const RtxMaterial& smat = sc.mats[sc.items[sh.item].d.material];
+                V3 shp = r.o + (r.d * sh.t);
+                float suv[2]; item_get_uv(sc, item, shp, sh.face, suv);                        // receiver's get_uv (sic, :905)
+                V4 satc; if (get_tex_color(sc, smat, suv, RTX_TEX_ALPHA, &satc)) shadow_source_alpha *= satc.x;
+                o.k = 1.0f * (1.0f - shadow_source_alpha);
+                o.occluder_index = sh.item; o.t = sh.t; o.face_id = sh.face;
+            }
+            out[i] = o;
         }
     });
     for (auto& t : th) t.join();

@@ -79,7 +79,8 @@ class RtxStats(C.Structure):
                 ("item_tests", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("waves", C.c_uint32), ("batches", C.c_uint32),
                 ("device_ms", C.c_float), ("closest_ms", C.c_float), ("shadow_ms", C.c_float), ("shade_ms", C.c_float),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("rays_shadow_skipped", C.c_uint64)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("rays_shadow_skipped", C.c_uint64),
+                ("host_syncs", C.c_uint32), ("reserved", C.c_uint32)]
 
     def as_dict(self) -> dict:
         return {k: (list(getattr(self, k)) if hasattr(getattr(self, k), '__len__') else getattr(self, k)) for k, _ in self._fields_}
@@ -92,6 +93,11 @@ class RtxRay(C.Structure):
 class RtxHit(C.Structure):
     _fields_ = [("t", C.c_float), ("normal", c_f3), ("item_id", C.c_uint32), ("face_id", C.c_uint32),
                 ("item_index", C.c_int32), ("reserved", C.c_uint32)]
+
+
+class RtxShadowHit(C.Structure):
+    _fields_ = [("k", C.c_float), ("lit", C.c_int32), ("occluder_index", C.c_int32), ("t", C.c_float),
+                ("face_id", C.c_uint32), ("reserved", C.c_uint32 * 3)]
 
 
 class RtxBvhInfo(C.Structure):
@@ -107,6 +113,9 @@ class RtxItemXform(C.Structure):
 HIT_DTYPE = np.dtype([("t", "<f4"), ("normal", "<f4", 3), ("item_id", "<u4"), ("face_id", "<u4"),
                       ("item_index", "<i4"), ("reserved", "<u4")])
 RAY_DTYPE = np.dtype([("origin", "<f4", 3), ("dir", "<f4", 3)])
+SHADOW_HIT_DTYPE = np.dtype([("k", "<f4"), ("lit", "<i4"), ("occluder_index", "<i4"), ("t", "<f4"), ("face_id", "<u4"),
+                             ("reserved", "<u4", 3)])
+assert SHADOW_HIT_DTYPE.itemsize == C.sizeof(RtxShadowHit)
 assert HIT_DTYPE.itemsize == C.sizeof(RtxHit) and RAY_DTYPE.itemsize == C.sizeof(RtxRay)
 
 
@@ -286,11 +295,23 @@ def bind(lib: C.CDLL, prefix: str = "rtx_") -> None:
                                  C.c_void_p, C.c_void_p, C.c_void_p]),
         "shard_unpack": (C.c_int, [C.c_uint32, C.c_uint32, P(RtxShard), C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+        "shard_unpack_all": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+        "bandwidth_probe": (C.c_int, [C.c_int, C.c_uint64, C.c_uint32, P(C.c_float)]),
         "render_frame_async": (C.c_int, [C.c_void_p, P(RtxCamera), P(RtxConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
         "render_poll": (C.c_int, [C.c_void_p, P(C.c_uint64), P(C.c_int), P(C.c_int), P(C.c_int), P(RtxStats)]),
         "render_stop": (C.c_int, [C.c_void_p]),
         "render_snapshot": (C.c_int, [C.c_void_p, P(C.c_uint64)]),
         "trace_probe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_uint32, C.c_void_p]),
+        "shadow_probe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]),
+        "scene_create_multi": (C.c_int, [P(RtxSceneDesc), P(C.c_int), C.c_uint32, P(C.c_void_p)]),
+        "scene_device_count": (C.c_int, [C.c_void_p]),
+        "gbuffer_create": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, P(C.c_void_p)]),
+        "gbuffer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+        "gbuffer_open": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, P(C.c_void_p)]),
+        "gbuffer_pointers": (C.c_int, [C.c_void_p, P(C.c_void_p), P(C.c_void_p), P(C.c_void_p), P(C.c_void_p)]),
+        "gbuffer_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+        "gbuffer_destroy": (C.c_int, [C.c_void_p]),
         "sample_table": (C.c_int, [C.c_uint32, P(C.c_uint32), C.c_void_p]),
         "scene_bvh_info": (C.c_int, [C.c_void_p, P(RtxBvhInfo)]),
         "scene_destroy": (C.c_int, [C.c_void_p]),
@@ -311,7 +332,9 @@ ABI_SYMBOLS = ["rtx_scene_create", "rtx_scene_update_items", "rtx_scene_set_ligh
                "rtx_render_frame_device", "rtx_render_frame_async", "rtx_render_poll", "rtx_render_stop", "rtx_render_snapshot", "rtx_shard_pixel_count", "rtx_shard_packed_bytes", "rtx_shard_pack",
                "rtx_shard_unpack", "rtx_trace_probe", "rtx_sample_table", "rtx_scene_bvh_info",
                "rtx_scene_destroy", "rtx_last_error", "rtx_abi_version", "rtx_device_count",
-               "rtx_post_process_device"]
+               "rtx_post_process_device", "rtx_shadow_probe", "rtx_scene_create_multi", "rtx_scene_device_count",
+               "rtx_gbuffer_create", "rtx_gbuffer_export", "rtx_gbuffer_open", "rtx_gbuffer_pointers", "rtx_gbuffer_download",
+               "rtx_gbuffer_destroy", "rtx_shard_unpack_all", "rtx_bandwidth_probe"]
 
 
 def fixture_path(name: str) -> str:

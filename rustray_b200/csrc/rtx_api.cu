@@ -9,6 +9,18 @@
 // holding >= CHUNK rays, else a fresh batch of primary rays, else the shallowest non-empty queue;
 // that keeps every queue below 3*CHUNK without ever dropping or re-queueing a ray, and keeps waves
 // fat (a deep queue is only drained early when it is full).
+//
+// Sync-free frames.  When all primary rays of the (sharded) frame fit one wave the host never reads a
+// counter back: level d+1's ray count is the device counter level d's shade kernel appended to, every
+// kernel takes its count from device memory, and the whole frame is enqueued in one go (one stream
+// sync at the end).  A queue that would overflow raises a device flag and the frame is redone with the
+// synchronised schedule.  This is what a launch-bound frame (config 1) and a strong-scaled shard need.
+//
+// Multi-GPU in ONE process (rtx_scene_create_multi): the scene is replicated, every device renders the
+// interleaved tiles it owns on its own host thread, and its resolve kernel stores the finished pixels
+// straight into the frame buffers on the first device over NVLink peer memory — resolve and gather are
+// one kernel, there is no separate collective.  Across processes the same stores go through CUDA IPC
+// (rtx_gbuffer_*).
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -68,6 +80,13 @@ template <typename T> struct DevBuf {
         return RTX_OK;
     }
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    // device-to-device copy of another device's buffer (NVLink peer copy); the current device must be dst_dev
+    int clone_from(const DevBuf<T>& o, int src_dev, int dst_dev) {
+        int rc = alloc(std::max<size_t>(o.n, 1));
+        if (rc) return rc;
+        if (o.n) CU(cudaMemcpyPeer(p, dst_dev, o.p, src_dev, o.n * sizeof(T)));
+        return RTX_OK;
+    }
 };
 
 struct PixelList { DevBuf<uint32_t> d; uint32_t n = 0; };
@@ -95,7 +114,19 @@ struct RtxScene {
     DevBuf<float4> q_o, q_d; DevBuf<uint2> q_m;
     DevBuf<float4> s_o, s_d, s_c; DevBuf<uint32_t> s_r, s_slow;
     DevBuf<HitRec> hits; DevBuf<uint32_t> ctr_pool; DevBuf<uint32_t> overflow; DevBuf<Counters> counters;
-    uint32_t* h_ctr = nullptr;              // pinned, 4 uint32
+    uint32_t* h_ctr = nullptr;              // pinned: 4 uint32 per-wave read-back + 8 * 66 level counters of a sync-free frame
+    uint32_t wave_cap = 0;                  // rays one wave may hold (hit records, shadow queue / lights)
+    uint32_t n_enabled_lights = 0;          // host mirror (rtx_scene_create / rtx_scene_set_lights)
+    bool no_sync_free = false;              // a sync-free frame overflowed a queue once: keep the synchronised schedule
+    std::mutex api_mu;                      // serialises frames / updates on one handle
+    // rtx_trace_probe / rtx_shadow_probe: own stream, queues and counters, so a pick never touches a frame in flight
+    struct Probe {
+        cudaStream_t st = nullptr; uint32_t cap = 0; std::mutex mu;
+        DevBuf<float4> q_o, q_d, s_c, acc; DevBuf<uint2> q_m; DevBuf<uint32_t> s_r, slow, ctr; DevBuf<HitRec> hits; DevBuf<uint4> out;
+        DevBuf<float> len; DevBuf<int32_t> recv; DevBuf<ShadowProbeOut> res;
+    } probe;
+    // single-process multi-GPU: replicas[k] renders shard k+1 of `1 + replicas.size()` (this handle renders shard 0)
+    std::vector<RtxScene*> replicas; RtxScene* primary = nullptr; cudaStream_t own_stream = nullptr; cudaEvent_t fence = nullptr;
     std::vector<cudaEvent_t> events;
     int blocks_closest = 0, blocks_closest_st = 0, blocks_shadow = 0, blocks_shadow_st = 0;
     // host-output staging for rtx_render_frame
@@ -240,6 +271,8 @@ int get_pixel_list(RtxScene& sc, uint32_t w, uint32_t h, const RtxShard* shard, 
     pl->n = (uint32_t)px.size();
     int rc = pl->d.upload(px);
     if (rc) { delete pl; return rc; }
+    // the list is read by kernels on the caller's stream (possibly cudaStreamNonBlocking): finish the upload first
+    if (cudaStreamSynchronize(0) != cudaSuccess) { delete pl; return fail(RTX_E_CUDA, "pixel list upload failed"); }
     sc.pixel_lists[key] = pl;
     *out = pl;
     return RTX_OK;
@@ -293,21 +326,24 @@ int ensure_frame(RtxScene& sc, uint32_t w, uint32_t h) {
     return RTX_OK;
 }
 
-int ensure_queues(RtxScene& sc, uint32_t max_recursion, uint32_t n_lights_enabled) {
-    uint32_t levels = max_recursion + 1;
+// Queue sizing for ONE frame.  chunk = rays per wave: 8 Mi, less for a frame that has fewer primary rays (a 800x600x1
+// frame does not allocate gigabytes) and less when max_recursion is so high that levels * 3 * chunk * 40 B would pass 12 GB.
+// Everything is derived from THIS frame's (levels, chunk); the buffers only ever grow.
+int ensure_queues(RtxScene& sc, uint32_t max_recursion, uint32_t n_lights_enabled, uint64_t n_primary) {
+    const uint32_t levels = max_recursion + 1;
     if (levels > 64) return fail(RTX_E_INVALID, "max_recursion > 63 is not supported by the wavefront queues");
     uint32_t chunk = 1u << 23;                    // rays per wave: bigger waves = fewer kernel tails and host round trips
     if (const char* e = getenv("RTX_CHUNK")) { long v = atol(e); if (v >= 1024) chunk = (uint32_t)v; }
+    while (chunk > (1u << 16) && (uint64_t)(chunk >> 1) >= n_primary) chunk >>= 1;
     while (chunk > (1u << 17) && (size_t)levels * 3 * chunk * 40 > (size_t)12 << 30) chunk >>= 1;   // <= 12 GB of ray queues
-    uint32_t shadow_cap = chunk * std::max(1u, n_lights_enabled);
-    if (sc.chunk == chunk && sc.levels >= levels && sc.shadow_cap >= shadow_cap) return RTX_OK;
-    sc.chunk = chunk; sc.levels = std::max(sc.levels, levels); sc.level_cap = 3 * chunk; sc.shadow_cap = std::max(sc.shadow_cap, shadow_cap);
-    size_t qn = (size_t)sc.levels * sc.level_cap;
+    sc.chunk = chunk; sc.levels = levels; sc.level_cap = 3 * chunk; sc.wave_cap = 2 * chunk;
+    sc.shadow_cap = sc.wave_cap * std::max(1u, n_lights_enabled);
+    const size_t qn = (size_t)levels * sc.level_cap;
     int rc;
     if ((rc = sc.q_o.alloc(qn)) || (rc = sc.q_d.alloc(qn)) || (rc = sc.q_m.alloc(qn))) return rc;
     if ((rc = sc.s_o.alloc(sc.shadow_cap)) || (rc = sc.s_d.alloc(sc.shadow_cap)) || (rc = sc.s_c.alloc(sc.shadow_cap)) || (rc = sc.s_r.alloc(sc.shadow_cap)) || (rc = sc.s_slow.alloc(sc.shadow_cap))) return rc;
-    if ((rc = sc.hits.alloc(chunk)) || (rc = sc.ctr_pool.alloc(kCtrPool)) || (rc = sc.overflow.alloc(4)) || (rc = sc.counters.alloc(1))) return rc;
-    if (!sc.h_ctr) CU(cudaMallocHost(&sc.h_ctr, 16));
+    if ((rc = sc.hits.alloc(sc.wave_cap)) || (rc = sc.ctr_pool.alloc(kCtrPool)) || (rc = sc.overflow.alloc(4)) || (rc = sc.counters.alloc(1))) return rc;
+    if (!sc.h_ctr) CU(cudaMallocHost(&sc.h_ctr, (4 + 8 * 66) * sizeof(uint32_t)));
     return RTX_OK;
 }
 
@@ -509,6 +545,9 @@ int rtx_scene_create(const RtxSceneDesc* d, int device, RtxScene** out) {
     CU(cudaDeviceSynchronize());
     refresh_dev(*sc);
     sc->dev.n_lights = d->n_lights;
+    sc->n_enabled_lights = 0;
+    for (uint32_t i = 0; i < d->n_lights; i++) if (d->lights[i].enabled) sc->n_enabled_lights++;
+    { int rc2 = occupancy_blocks(*sc); if (rc2) { std::string keep = g_err; rtx_scene_destroy(sc); g_err = keep; return rc2; } }
     sc->build_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     *out = sc;
     return RTX_OK;
@@ -518,8 +557,18 @@ int rtx_scene_destroy(RtxScene* sc) {
     if (!sc) return RTX_OK;
     sc->cancel.store(true);
     if (sc->worker.joinable()) sc->worker.join();
+    for (RtxScene* r : sc->replicas) rtx_scene_destroy(r);
+    sc->replicas.clear();
     cudaSetDevice(sc->device);
     cudaDeviceSynchronize();
+    {
+        RtxScene::Probe& P = sc->probe;
+        P.q_o.release(); P.q_d.release(); P.s_c.release(); P.acc.release(); P.q_m.release(); P.s_r.release(); P.slow.release(); P.ctr.release();
+        P.hits.release(); P.out.release(); P.len.release(); P.recv.release(); P.res.release();
+        if (P.st) cudaStreamDestroy(P.st);
+    }
+    if (sc->own_stream) cudaStreamDestroy(sc->own_stream);
+    if (sc->fence) cudaEventDestroy(sc->fence);
     sc->nodes.release(); sc->tris.release(); sc->items.release(); sc->tlas_prims.release();
     sc->verts.release(); sc->uvs.release(); sc->nrms.release(); sc->idx.release(); sc->uv_idx.release(); sc->n_idx.release();
     sc->mats.release(); sc->texs.release(); sc->texels.release(); sc->lights.release();
@@ -536,6 +585,12 @@ int rtx_scene_destroy(RtxScene* sc) {
 
 int rtx_scene_update_items(RtxScene* sc, const RtxItemXform* x, size_t n) {
     if (!sc || (!x && n)) return fail(RTX_E_INVALID, "null argument");
+    // the reference takes the scene's RwLock for writing here (run.rs); a frame in flight holds it for reading
+    if (sc->running.load()) return fail(RTX_E_BUSY, "a frame is in flight on this handle");
+    std::unique_lock<std::mutex> lk(sc->api_mu, std::defer_lock);
+    if (!sc->primary) lk.lock();
+    std::lock_guard<std::mutex> plk(sc->probe.mu);
+    for (RtxScene* r : sc->replicas) { int rc = rtx_scene_update_items(r, x, n); if (rc) return rc; }
     CU(cudaSetDevice(sc->device));
     for (size_t i = 0; i < n; i++) {
         if (x[i].item_index >= sc->src_items.size()) return fail(RTX_E_INVALID, "item index out of range");
@@ -569,6 +624,10 @@ int rtx_scene_update_items(RtxScene* sc, const RtxItemXform* x, size_t n) {
 
 int rtx_scene_set_lights(RtxScene* sc, const RtxLight* l, uint32_t n) {
     if (!sc || (!l && n)) return fail(RTX_E_INVALID, "null argument");
+    if (sc->running.load()) return fail(RTX_E_BUSY, "a frame is in flight on this handle");
+    std::unique_lock<std::mutex> lk(sc->api_mu, std::defer_lock);
+    if (!sc->primary) lk.lock();
+    for (RtxScene* r : sc->replicas) { int rc = rtx_scene_set_lights(r, l, n); if (rc) return rc; }
     CU(cudaSetDevice(sc->device));
     std::vector<DLight> h; fill_lights(l, n, h);
     CU(cudaDeviceSynchronize());
@@ -576,6 +635,8 @@ int rtx_scene_set_lights(RtxScene* sc, const RtxLight* l, uint32_t n) {
     CU(cudaDeviceSynchronize());
     refresh_dev(*sc);
     sc->dev.n_lights = n;
+    sc->n_enabled_lights = 0;
+    for (uint32_t i = 0; i < n; i++) if (l[i].enabled) sc->n_enabled_lights++;
     return RTX_OK;
 }
 
@@ -589,27 +650,103 @@ int rtx_scene_bvh_info(const RtxScene* sc, RtxBvhInfo* info) {
 }
 
 // ---- the frame ------------------------------------------------------------------------------------
-int rtx_render_frame_device(RtxScene* sc, const RtxCamera* cam, const RtxConfig* cfg, const RtxShard* shard, void* d_rgba, void* d_normals,
-                            void* d_depth, void* d_object_ids, void* cuda_stream, RtxStats* stats) {
-    if (!sc || !cam || !cfg) return fail(RTX_E_INVALID, "null argument");
-    if (cam->width == 0 || cam->height == 0 || (uint64_t)cam->width * cam->height > 0x7fffffffull) return fail(RTX_E_INVALID, "bad frame size");
-    if (cfg->samples == 0 || cfg->samples > 65535) return fail(RTX_E_INVALID, "samples out of range (u16)");
-    if (cfg->max_recursion > 254) return fail(RTX_E_INVALID, "max_recursion > 254 is not supported");
+}  // extern "C"
+
+namespace {
+
+struct FrameCtx {
+    RtxScene* sc; cudaStream_t st; FrameDev F; PixelList* pl; const RtxConfig* cfg; const RtxCamera* cam;
+    void *d_rgba, *d_normals, *d_depth, *d_ids;
+    bool want_stats, ordered, primary_single = false; uint32_t L; int gs;
+    uint64_t launches = 0, rays_closest = 0, rays_shadow = 0, primary = 0; uint32_t waves = 0, batches = 0; size_t ev_next = 2;
+    cudaEvent_t event(size_t i) {
+        while (sc->events.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); sc->events.push_back(e); }
+        return sc->events[i];
+    }
+};
+
+// One wave at depth d: closest -> shade -> shadow.  n_ptr == nullptr: n rays at q_base (count known on the host);
+// otherwise the count is read on the device (at most n).  ctr = this wave's 8 counters.
+int launch_wave(FrameCtx& X, uint32_t d, uint32_t q_base, uint32_t n, const uint32_t* n_ptr, uint32_t* ctr, uint32_t child_off) {
+    RtxScene* sc = X.sc; cudaStream_t st = X.st;
+    RayQ Q = level_queue(*sc, d);
+    ShadowQ SQ{sc->s_o.p, sc->s_d.p, sc->s_c.p, sc->s_r.p, nullptr};
+    cudaEvent_t e0 = X.event(X.ev_next), e1 = X.event(X.ev_next + 1), e2 = X.event(X.ev_next + 2), e3 = X.event(X.ev_next + 3);
+    X.ev_next += 4;
+    const bool verify = !n_ptr && getenv("RTX_VERIFY");
+    if (verify) cudaMemsetAsync(sc->hits.p, 0xEE, (size_t)n * sizeof(HitRec), st);
+    CU(cudaEventRecord(e0, st));
+    {
+        const int maxb = X.want_stats ? sc->blocks_closest_st : sc->blocks_closest;
+        const uint32_t warps = (n + 31) / 32;
+        const int blocks = n_ptr ? maxb : (int)std::min<uint32_t>((warps + (kTraceBlock / 32) - 1) / (kTraceBlock / 32), (uint32_t)maxb);
+        if (X.want_stats) closest_kernel<true><<<blocks, kTraceBlock, 0, st>>>(sc->dev, Q, q_base, n, n_ptr, sc->hits.p, ctr, sc->counters.p);
+        else closest_kernel<false><<<blocks, kTraceBlock, 0, st>>>(sc->dev, Q, q_base, n, n_ptr, sc->hits.p, ctr, sc->counters.p);
+        X.launches++;
+    }
+    CU(cudaEventRecord(e1, st));
+    if (verify) {
+        static uint32_t* d_cnt = nullptr; static VerifyRec* d_rec = nullptr;
+        if (!d_cnt) { cudaMalloc(&d_cnt, 4); cudaMalloc(&d_rec, 64 * sizeof(VerifyRec)); }
+        cudaMemsetAsync(d_cnt, 0, 4, st);
+        verify_closest_kernel<<<(n + 127) / 128, 128, 0, st>>>(sc->dev, Q, q_base, n, sc->hits.p, d_cnt, d_rec, 64);
+        uint32_t hc = 0; VerifyRec hr[64];
+        cudaMemcpyAsync(&hc, d_cnt, 4, cudaMemcpyDeviceToHost, st); cudaStreamSynchronize(st);
+        if (hc) {
+            cudaMemcpy(hr, d_rec, sizeof(hr), cudaMemcpyDeviceToHost);
+            uint32_t ovf[4]; cudaMemcpy(ovf, sc->overflow.p, 16, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[RTX_VERIFY] wave %u depth %u n %u: %u mismatching closest hits (queue overflow %u, lane stack overflow %u) err=%s\n", X.waves, d, n, hc, ovf[0], ovf[1], cudaGetErrorString(cudaGetLastError()));
+            for (uint32_t k = 0; k < std::min(hc, 40u); k++)
+                fprintf(stderr, "   idx %u o %.9g %.9g %.9g d %.9g %.9g %.9g depth %u | prod t %.9g item %x prim %u | ref t %.9g item %d prim %u\n", hr[k].index, hr[k].o[0], hr[k].o[1],
+                        hr[k].o[2], hr[k].d[0], hr[k].d[1], hr[k].d[2], hr[k].depth, hr[k].t_prod, (int)hr[k].item_prod, hr[k].prim_prod, hr[k].t_ref,
+                        (int)hr[k].item_ref, hr[k].prim_ref);
+        }
+    }
+    {
+        ShadeOut so;
+        const bool spawn = d + 1 <= X.L;                                  // depth L never spawns children (depth <= max_recursion fails)
+        RayQ C = level_queue(*sc, spawn ? d + 1 : d);
+        const uint32_t off = spawn ? child_off : 0;
+        so.child = RayQ{C.o + off, C.d + off, C.m + off};
+        // a sync-free level is consumed by ONE wave, so it may not hold more than a wave
+        so.child_cap = spawn ? (n_ptr || X.primary_single ? std::min(sc->level_cap - off, sc->wave_cap) : sc->level_cap - off) : 0;
+        so.child_count = ctr + 2;
+        so.shadow = SQ; so.shadow_cap = sc->shadow_cap; so.shadow_count = ctr + 3; so.overflow = sc->overflow.p; so.skipped = sc->overflow.p + 2;
+        const int blocks = (int)std::min<uint32_t>((n + kShadeBlock - 1) / kShadeBlock, (uint32_t)sc->sm_count * 16);
+        shade_kernel<<<blocks, kShadeBlock, 0, st>>>(sc->dev, X.F, Q, q_base, n, n_ptr, sc->hits.p, so);
+        X.launches++;
+    }
+    CU(cudaEventRecord(e2, st));
+    if (sc->n_enabled_lights > 0) {
+        const int eb = sc->sm_count * 8;
+        if (X.ordered) {
+            shadow_exact_kernel<false, true><<<eb, kTraceBlock, 0, st>>>(sc->dev, X.F, SQ, nullptr, ctr + 3, sc->shadow_cap, d, sc->counters.p);
+            X.launches++;
+        } else {
+            if (X.want_stats) shadow_any_kernel<true><<<sc->blocks_shadow_st, kTraceBlock, 0, st>>>(sc->dev, X.F, SQ, ctr + 3, sc->shadow_cap, d, ctr + 1, sc->s_slow.p, ctr + 4, sc->counters.p);
+            else shadow_any_kernel<false><<<sc->blocks_shadow, kTraceBlock, 0, st>>>(sc->dev, X.F, SQ, ctr + 3, sc->shadow_cap, d, ctr + 1, sc->s_slow.p, ctr + 4, sc->counters.p);
+            if (X.want_stats) shadow_exact_kernel<true, false><<<eb, kTraceBlock, 0, st>>>(sc->dev, X.F, SQ, sc->s_slow.p, ctr + 4, sc->shadow_cap, d, sc->counters.p);
+            else shadow_exact_kernel<false, false><<<eb, kTraceBlock, 0, st>>>(sc->dev, X.F, SQ, sc->s_slow.p, ctr + 4, sc->shadow_cap, d, sc->counters.p);
+            X.launches += 2;
+        }
+    }
+    CU(cudaEventRecord(e3, st));
+    return RTX_OK;
+}
+
+// The frame of ONE device (its shard of the pixels).  Outputs may be peer memory (another device's frame buffers).
+int render_frame_single(RtxScene* sc, const RtxCamera* cam, const RtxConfig* cfg, const RtxShard* shard, void* d_rgba, void* d_normals,
+                        void* d_depth, void* d_object_ids, cudaStream_t st, RtxStats* stats) {
     CU(cudaSetDevice(sc->device));
-    cudaStream_t st = (cudaStream_t)cuda_stream;
-    const bool want_stats = cfg->debug_flags & RTX_DEBUG_COLLECT_STATS, ordered = cfg->debug_flags & RTX_DEBUG_ORDERED_SHADOW;
+    FrameCtx X; X.sc = sc; X.st = st; X.cfg = cfg; X.cam = cam; X.d_rgba = d_rgba; X.d_normals = d_normals; X.d_depth = d_depth; X.d_ids = d_object_ids;
+    X.want_stats = cfg->debug_flags & RTX_DEBUG_COLLECT_STATS; X.ordered = cfg->debug_flags & RTX_DEBUG_ORDERED_SHADOW;
     int rc;
     PixelList* pl;
     if ((rc = get_pixel_list(*sc, cam->width, cam->height, shard, &pl))) return rc;
+    X.pl = pl;
     if ((rc = ensure_frame(*sc, cam->width, cam->height))) return rc;
-    uint32_t n_enabled = 0;
-    {
-        // enabled lights are counted on the host copy of the device lights
-        std::vector<DLight> hl(sc->dev.n_lights);
-        if (!hl.empty()) CU(cudaMemcpy(hl.data(), sc->lights.p, hl.size() * sizeof(DLight), cudaMemcpyDeviceToHost));
-        for (auto& l : hl) if (l.enabled) n_enabled++;
-    }
-    if ((rc = ensure_queues(*sc, cfg->max_recursion, n_enabled))) return rc;
+    const uint64_t n_primary = (uint64_t)pl->n * cfg->samples;
+    if ((rc = ensure_queues(*sc, cfg->max_recursion, sc->n_enabled_lights, n_primary))) return rc;
     if ((rc = occupancy_blocks(*sc))) return rc;
     uint64_t h2d = 0;
     if (sc->table_samples != cfg->samples) {
@@ -617,7 +754,7 @@ int rtx_render_frame_device(RtxScene* sc, const RtxCamera* cam, const RtxConfig*
         if ((rc = sc->sample_table.upload(t, st))) return rc;
         sc->table_samples = cfg->samples; h2d += t.size() * 4;
     }
-    FrameDev F; memset(&F, 0, sizeof(F));
+    FrameDev& F = X.F; memset(&F, 0, sizeof(F));
     memcpy(F.pinv, cam->projection_inverse, 64); memcpy(F.vinv, cam->view_inverse, 64);
     F.width = cam->width; F.height = cam->height; F.n_samples = cfg->samples; F.cell_size = sc->cell_size;
     F.monte_carlo = cfg->monte_carlo; F.max_recursion = cfg->max_recursion; F.gamma = cfg->gamma_correction; F.mc_seed = cfg->mc_seed;
@@ -629,181 +766,160 @@ int rtx_render_frame_device(RtxScene* sc, const RtxCamera* cam, const RtxConfig*
     F.sample_table = sc->sample_table.p; F.accum_c = sc->accum_c.p; F.accum_n = sc->accum_n.p; F.ids = sc->ids.p;
     h2d += sizeof(FrameDev);                                             // kernel parameters (camera + config)
 
-    // events: [0] frame start, [1] frame end, then 4 per wave (closest start/end, shadow start/end)
-    auto get_event = [&](size_t i) -> cudaEvent_t {
-        while (sc->events.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); sc->events.push_back(e); }
-        return sc->events[i];
-    };
-    size_t ev_next = 2;
-    CU(cudaEventRecord(get_event(0), st));
-    CU(cudaMemsetAsync(sc->ctr_pool.p, 0, kCtrPool * 4, st));
-    CU(cudaMemsetAsync(sc->overflow.p, 0, 16, st));
-    if (want_stats) CU(cudaMemsetAsync(sc->counters.p, 0, sizeof(Counters), st));
-    uint64_t launches = 0;
-    const int gs = sc->sm_count * 8;
-    clear_pixels_kernel<<<gs, 256, 0, st>>>(F, pl->d.p, pl->n); launches++;
-
     const uint32_t L = cfg->max_recursion + 1;                           // deepest ray depth
-    std::vector<uint32_t> counts(L + 2, 0);
+    X.L = L; X.gs = sc->sm_count * 8;
+    const int gs = X.gs;
     const uint32_t chunk = sc->chunk;
-    // primary batches: pixel ranges of <= chunk pixels x sample ranges so that np*ns <= chunk
-    // Batch geometry: as many samples of a pixel as fit (all of them up to 128 spp) rather than few samples of every pixel —
-    // the rays of one pixel then travel through the waves together (BVH, texture and accumulator locality: -2 % frame time on
-    // config 2), and pixels finish in order, which is what the progressive display wants.
-    uint32_t np_cap = std::min(chunk, std::max(65536u, chunk / std::max(1u, cfg->samples)));
-    if (const char* e = getenv("RTX_BATCH_PIXELS")) np_cap = std::max(1, atoi(e));
-    const uint32_t np_full = std::min(pl->n, np_cap);
-    const uint32_t ns_full = std::max(1u, chunk / std::max(1u, np_full));
-    uint32_t cur_p0 = 0, cur_s0 = 0;
-    bool primary_left = pl->n > 0;
-    uint32_t ctr_idx = 0, waves = 0, batches = 0;
-    uint64_t rays_closest = 0, rays_shadow = 0, primary = 0;
-    ShadowQ SQ{sc->s_o.p, sc->s_d.p, sc->s_c.p, sc->s_r.p};
+    bool sync_free = n_primary <= chunk && !sc->no_sync_free && !getenv("RTX_FORCE_SYNC") && !getenv("RTX_VERIFY");
+    uint32_t ovf[4] = {0, 0, 0, 0};
 
-    for (;;) {
-        if (sc->cancel.load(std::memory_order_relaxed)) { CU(cudaStreamSynchronize(st)); return fail(RTX_E_CANCELLED, "frame cancelled by rtx_render_stop"); }
-        if (sc->snap_req.load(std::memory_order_relaxed)) {
-            // progressive preview (the stream is idle here): pixels whose samples were all issued are normalised by the sample
-            // count, the pixel range in progress by the samples issued so far, the rest is cleared; rays still queued at
-            // deeper levels are simply not in the sums yet
-            const size_t npx = (size_t)cam->width * cam->height;
-            if (d_rgba) CU(cudaMemsetAsync(d_rgba, 0, npx * 4, st));
-            if (d_normals) CU(cudaMemsetAsync(d_normals, 0, npx * 12, st));
-            if (d_depth) CU(cudaMemsetAsync(d_depth, 0, npx * 4, st));
-            if (d_object_ids) CU(cudaMemsetAsync(d_object_ids, 0, npx * 4, st));
-            const uint32_t done_px = primary_left ? cur_p0 : pl->n;
-            if (done_px) resolve_kernel<<<std::min<uint32_t>((done_px + 255) / 256, gs), 256, 0, st>>>(F, pl->d.p, done_px, (uchar4*)d_rgba, (float*)d_normals,
-                                                                                                    (float*)d_depth, (uint32_t*)d_object_ids);
-            if (primary_left && cur_s0 > 0) {
-                FrameDev Fp = F; Fp.n_samples = cur_s0;
-                const uint32_t np = std::min(np_full, pl->n - cur_p0);
-                resolve_kernel<<<std::min<uint32_t>((np + 255) / 256, gs), 256, 0, st>>>(Fp, pl->d.p + cur_p0, np, (uchar4*)d_rgba, (float*)d_normals, (float*)d_depth,
-                                                                                       (uint32_t*)d_object_ids);
+    for (int attempt = 0; attempt < 2; attempt++) {
+        X.launches = 0; X.rays_closest = X.rays_shadow = X.primary = 0; X.waves = X.batches = 0; X.ev_next = 2;
+        X.primary_single = sync_free;
+        // events: [0] frame start, [1] frame end, then 4 per wave (closest start/end, shadow start/end)
+        CU(cudaEventRecord(X.event(0), st));
+        CU(cudaMemsetAsync(sc->ctr_pool.p, 0, kCtrPool * 4, st));
+        CU(cudaMemsetAsync(sc->overflow.p, 0, 16, st));
+        if (X.want_stats) CU(cudaMemsetAsync(sc->counters.p, 0, sizeof(Counters), st));
+        clear_pixels_kernel<<<gs, 256, 0, st>>>(F, pl->d.p, pl->n); X.launches++;
+
+        if (sync_free) {
+            // ---- the whole frame in one go: level d+1's count is level d's child counter, never seen by the host ----
+            if (sc->cancel.load(std::memory_order_relaxed)) { CU(cudaStreamSynchronize(st)); return fail(RTX_E_CANCELLED, "frame cancelled by rtx_render_stop"); }
+            const uint32_t n1 = (uint32_t)n_primary;
+            if (n1) { raygen_kernel<<<std::min<uint32_t>((n1 + 255) / 256, gs), 256, 0, st>>>(F, pl->d.p, 0, pl->n, 0, cfg->samples, level_queue(*sc, 1), 0); X.launches++; X.batches++; }
+            X.primary = n1;
+            sc->samples_issued.store(n1, std::memory_order_relaxed);
+            for (uint32_t d = 1; d <= L && n1; d++) {
+                uint32_t* ctr = sc->ctr_pool.p + 8 * d;                   // block d: [2] = rays appended to level d+1
+                if ((rc = launch_wave(X, d, 0, d == 1 ? n1 : sc->wave_cap, d == 1 ? nullptr : ctr - 8 + 2, ctr, 0))) return rc;
+                X.waves++;
             }
-            if (sc->snap_rgba && d_rgba) CU(cudaMemcpyAsync(sc->snap_rgba, d_rgba, npx * 4, cudaMemcpyDeviceToHost, st));
-            if (sc->snap_normals && d_normals) CU(cudaMemcpyAsync(sc->snap_normals, d_normals, npx * 12, cudaMemcpyDeviceToHost, st));
-            if (sc->snap_depth && d_depth) CU(cudaMemcpyAsync(sc->snap_depth, d_depth, npx * 4, cudaMemcpyDeviceToHost, st));
-            if (sc->snap_ids && d_object_ids) CU(cudaMemcpyAsync(sc->snap_ids, d_object_ids, npx * 4, cudaMemcpyDeviceToHost, st));
+            resolve_kernel<<<std::min<uint32_t>((pl->n + 255) / 256, gs), 256, 0, st>>>(F, pl->d.p, pl->n, (uchar4*)d_rgba, (float*)d_normals, (float*)d_depth,
+                                                                                    (uint32_t*)d_object_ids);
+            X.launches++;
+            CU(cudaEventRecord(X.event(1), st));
+            CU(cudaMemcpyAsync(sc->h_ctr + 4, sc->ctr_pool.p, (size_t)8 * (L + 1) * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(sc->h_ctr, sc->overflow.p, 16, cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
-            { std::lock_guard<std::mutex> lk(sc->snap_mu); sc->snap_seq++; sc->snap_req.store(0); }
-            sc->snap_cv.notify_all();
-        }
-        int level = -1;
-        for (int d = (int)L; d >= 1; d--) if (counts[d] >= chunk) { level = d; break; }
-        if (level < 0 && primary_left) level = 0;
-        if (level < 0) for (uint32_t d = 1; d <= L; d++) if (counts[d] > 0) { level = (int)d; break; }
-        if (level < 0) break;
-        if (level == 0) {
-            const uint32_t np = std::min(np_full, pl->n - cur_p0), ns = std::min(ns_full, cfg->samples - cur_s0);
-            const uint32_t n = np * ns;
-            raygen_kernel<<<std::min<uint32_t>((n + 255) / 256, gs), 256, 0, st>>>(F, pl->d.p, cur_p0, np, cur_s0, ns, level_queue(*sc, 1), counts[1]);
-            launches++; batches++;
-            counts[1] += n; primary += n;
-            sc->samples_issued.store(primary, std::memory_order_relaxed);
-            cur_s0 += ns;
-            if (cur_s0 >= cfg->samples) { cur_s0 = 0; cur_p0 += np; if (cur_p0 >= pl->n) primary_left = false; }
-            continue;
-        }
-        // ---- one wave at depth `level` ----
-        const uint32_t d = (uint32_t)level;
-        const uint32_t n = std::min(counts[d], chunk);
-        const uint32_t q_base = counts[d] - n;
-        counts[d] -= n;
-        if (ctr_idx + 8 > kCtrPool) {                                    // stream is idle here (we sync every wave)
-            CU(cudaMemsetAsync(sc->ctr_pool.p, 0, kCtrPool * 4, st)); ctr_idx = 0;
-        }
-        uint32_t* ctr = sc->ctr_pool.p + ctr_idx; ctr_idx += 8;          // [0] closest work, [1] shadow work, [2] child count, [3] shadow count, [4] slow count
-        RayQ Q = level_queue(*sc, d);
-        const uint32_t warps = (n + 31) / 32;
-        cudaEvent_t e0 = get_event(ev_next), e1 = get_event(ev_next + 1), e2 = get_event(ev_next + 2), e3 = get_event(ev_next + 3);
-        ev_next += 4;
-        if (getenv("RTX_VERIFY")) cudaMemsetAsync(sc->hits.p, 0xEE, (size_t)n * sizeof(HitRec), st);
-        CU(cudaEventRecord(e0, st));
-        {
-            const int maxb = want_stats ? sc->blocks_closest_st : sc->blocks_closest;
-            const int blocks = (int)std::min<uint32_t>((warps + (kTraceBlock / 32) - 1) / (kTraceBlock / 32), (uint32_t)maxb);
-            if (want_stats) closest_kernel<true><<<blocks, kTraceBlock, 0, st>>>(sc->dev, Q, q_base, n, sc->hits.p, ctr, sc->counters.p);
-            else closest_kernel<false><<<blocks, kTraceBlock, 0, st>>>(sc->dev, Q, q_base, n, sc->hits.p, ctr, sc->counters.p);
-            launches++;
-        }
-        CU(cudaEventRecord(e1, st));
-        if (getenv("RTX_VERIFY")) {
-            static uint32_t* d_cnt = nullptr; static VerifyRec* d_rec = nullptr;
-            if (!d_cnt) { cudaMalloc(&d_cnt, 4); cudaMalloc(&d_rec, 64 * sizeof(VerifyRec)); }
-            cudaMemsetAsync(d_cnt, 0, 4, st);
-            verify_closest_kernel<<<(n + 127) / 128, 128, 0, st>>>(sc->dev, Q, q_base, n, sc->hits.p, d_cnt, d_rec, 64);
-            uint32_t hc = 0; VerifyRec hr[64];
-            cudaMemcpyAsync(&hc, d_cnt, 4, cudaMemcpyDeviceToHost, st); cudaStreamSynchronize(st);
-            if (hc) {
-                cudaMemcpy(hr, d_rec, sizeof(hr), cudaMemcpyDeviceToHost);
-                uint32_t ovf[4]; cudaMemcpy(ovf, sc->overflow.p, 16, cudaMemcpyDeviceToHost);
-                fprintf(stderr, "[RTX_VERIFY] wave %u depth %u n %u: %u mismatching closest hits (queue overflow %u, lane stack overflow %u) err=%s\n", waves, d, n, hc, ovf[0], ovf[1], cudaGetErrorString(cudaGetLastError()));
-                for (uint32_t k = 0; k < std::min(hc, 40u); k++)
-                    fprintf(stderr, "   idx %u o %.9g %.9g %.9g d %.9g %.9g %.9g depth %u | prod t %.9g item %x prim %u | ref t %.9g item %d prim %u\n", hr[k].index, hr[k].o[0], hr[k].o[1],
-                            hr[k].o[2], hr[k].d[0], hr[k].d[1], hr[k].d[2], hr[k].depth, hr[k].t_prod, (int)hr[k].item_prod, hr[k].prim_prod, hr[k].t_ref,
-                            (int)hr[k].item_ref, hr[k].prim_ref);
+            CU(cudaGetLastError());
+            memcpy(ovf, sc->h_ctr, 16);
+            if (ovf[0]) {                                                 // a level outgrew one wave: redo with the synchronised schedule
+                sc->no_sync_free = true; sync_free = false;
+                continue;
             }
-        }
-        {
-            ShadeOut so;
-            const uint32_t nd = d + 1 <= L ? d + 1 : d;                  // depth L never spawns children (depth <= max_recursion fails)
-            RayQ C = level_queue(*sc, nd);
-            const uint32_t off = d + 1 <= L ? counts[d + 1] : 0;
-            so.child = RayQ{C.o + off, C.d + off, C.m + off};
-            so.child_cap = d + 1 <= L ? sc->level_cap - off : 0;
-            so.child_count = ctr + 2;
-            so.shadow = SQ; so.shadow_cap = sc->shadow_cap; so.shadow_count = ctr + 3; so.overflow = sc->overflow.p; so.skipped = sc->overflow.p + 2;
-            const int blocks = (int)std::min<uint32_t>((n + kShadeBlock - 1) / kShadeBlock, (uint32_t)sc->sm_count * 16);
-            shade_kernel<<<blocks, kShadeBlock, 0, st>>>(sc->dev, F, Q, q_base, n, sc->hits.p, so);
-            launches++;
-        }
-        CU(cudaEventRecord(e2, st));
-        if (n_enabled > 0) {
-            const int eb = sc->sm_count * 8;
-            if (ordered) {
-                shadow_exact_kernel<false, true><<<eb, kTraceBlock, 0, st>>>(sc->dev, F, SQ, nullptr, ctr + 3, d, sc->counters.p);
-                launches++;
-            } else {
-                if (want_stats) shadow_any_kernel<true><<<sc->blocks_shadow_st, kTraceBlock, 0, st>>>(sc->dev, F, SQ, ctr + 3, d, ctr + 1, sc->s_slow.p, ctr + 4, sc->counters.p);
-                else shadow_any_kernel<false><<<sc->blocks_shadow, kTraceBlock, 0, st>>>(sc->dev, F, SQ, ctr + 3, d, ctr + 1, sc->s_slow.p, ctr + 4, sc->counters.p);
-                if (want_stats) shadow_exact_kernel<true, false><<<eb, kTraceBlock, 0, st>>>(sc->dev, F, SQ, sc->s_slow.p, ctr + 4, d, sc->counters.p);
-                else shadow_exact_kernel<false, false><<<eb, kTraceBlock, 0, st>>>(sc->dev, F, SQ, sc->s_slow.p, ctr + 4, d, sc->counters.p);
-                launches += 2;
+            X.rays_closest = n1;
+            for (uint32_t d = 1; d <= L; d++) {
+                const uint32_t* c = sc->h_ctr + 4 + 8 * d;
+                if (d < L) X.rays_closest += c[2];
+                X.rays_shadow += c[3];
             }
+            break;
         }
-        CU(cudaEventRecord(e3, st));
-        CU(cudaMemcpyAsync(sc->h_ctr, ctr, 16, cudaMemcpyDeviceToHost, st));
+
+        // ---- synchronised schedule ----
+        std::vector<uint32_t> counts(L + 2, 0);
+        // primary batches: pixel ranges of <= chunk pixels x sample ranges so that np*ns <= chunk
+        // Batch geometry: as many samples of a pixel as fit (all of them up to 128 spp) rather than few samples of every pixel —
+        // the rays of one pixel then travel through the waves together (BVH, texture and accumulator locality: -2 % frame time on
+        // config 2), and pixels finish in order, which is what the progressive display wants.
+        uint32_t np_cap = std::min(chunk, std::max(65536u, chunk / std::max(1u, cfg->samples)));
+        if (const char* e = getenv("RTX_BATCH_PIXELS")) np_cap = std::max(1, atoi(e));
+        const uint32_t np_full = std::min(pl->n, np_cap);
+        const uint32_t ns_full = std::max(1u, chunk / std::max(1u, np_full));
+        uint32_t cur_p0 = 0, cur_s0 = 0;
+        bool primary_left = pl->n > 0;
+        uint32_t ctr_idx = 0;
+        for (;;) {
+            if (sc->cancel.load(std::memory_order_relaxed)) { CU(cudaStreamSynchronize(st)); return fail(RTX_E_CANCELLED, "frame cancelled by rtx_render_stop"); }
+            if (sc->snap_req.load(std::memory_order_relaxed)) {
+                // progressive preview (the stream is idle here): pixels whose samples were all issued are normalised by the sample
+                // count, the pixel range in progress by the samples issued so far, the rest is cleared; rays still queued at
+                // deeper levels are simply not in the sums yet
+                const size_t npx = (size_t)cam->width * cam->height;
+                if (d_rgba) CU(cudaMemsetAsync(d_rgba, 0, npx * 4, st));
+                if (d_normals) CU(cudaMemsetAsync(d_normals, 0, npx * 12, st));
+                if (d_depth) CU(cudaMemsetAsync(d_depth, 0, npx * 4, st));
+                if (d_object_ids) CU(cudaMemsetAsync(d_object_ids, 0, npx * 4, st));
+                const uint32_t done_px = primary_left ? cur_p0 : pl->n;
+                if (done_px) resolve_kernel<<<std::min<uint32_t>((done_px + 255) / 256, gs), 256, 0, st>>>(F, pl->d.p, done_px, (uchar4*)d_rgba, (float*)d_normals,
+                                                                                                        (float*)d_depth, (uint32_t*)d_object_ids);
+                if (primary_left && cur_s0 > 0) {
+                    FrameDev Fp = F; Fp.n_samples = cur_s0;
+                    const uint32_t np = std::min(np_full, pl->n - cur_p0);
+                    resolve_kernel<<<std::min<uint32_t>((np + 255) / 256, gs), 256, 0, st>>>(Fp, pl->d.p + cur_p0, np, (uchar4*)d_rgba, (float*)d_normals, (float*)d_depth,
+                                                                                           (uint32_t*)d_object_ids);
+                }
+                if (sc->snap_rgba && d_rgba) CU(cudaMemcpyAsync(sc->snap_rgba, d_rgba, npx * 4, cudaMemcpyDeviceToHost, st));
+                if (sc->snap_normals && d_normals) CU(cudaMemcpyAsync(sc->snap_normals, d_normals, npx * 12, cudaMemcpyDeviceToHost, st));
+                if (sc->snap_depth && d_depth) CU(cudaMemcpyAsync(sc->snap_depth, d_depth, npx * 4, cudaMemcpyDeviceToHost, st));
+                if (sc->snap_ids && d_object_ids) CU(cudaMemcpyAsync(sc->snap_ids, d_object_ids, npx * 4, cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+                { std::lock_guard<std::mutex> lk(sc->snap_mu); sc->snap_seq++; sc->snap_req.store(0); }
+                sc->snap_cv.notify_all();
+            }
+            int level = -1;
+            for (int d = (int)L; d >= 1; d--) if (counts[d] >= chunk) { level = d; break; }
+            if (level < 0 && primary_left) level = 0;
+            if (level < 0) for (uint32_t d = 1; d <= L; d++) if (counts[d] > 0) { level = (int)d; break; }
+            if (level < 0) break;
+            if (level == 0) {
+                const uint32_t np = std::min(np_full, pl->n - cur_p0), ns = std::min(ns_full, cfg->samples - cur_s0);
+                const uint32_t n = np * ns;
+                raygen_kernel<<<std::min<uint32_t>((n + 255) / 256, gs), 256, 0, st>>>(F, pl->d.p, cur_p0, np, cur_s0, ns, level_queue(*sc, 1), counts[1]);
+                X.launches++; X.batches++;
+                counts[1] += n; X.primary += n;
+                sc->samples_issued.store(X.primary, std::memory_order_relaxed);
+                cur_s0 += ns;
+                if (cur_s0 >= cfg->samples) { cur_s0 = 0; cur_p0 += np; if (cur_p0 >= pl->n) primary_left = false; }
+                continue;
+            }
+            // ---- one wave at depth `level` ----
+            const uint32_t d = (uint32_t)level;
+            const uint32_t n = std::min(counts[d], chunk);
+            const uint32_t q_base = counts[d] - n;
+            counts[d] -= n;
+            if (ctr_idx + 8 > kCtrPool) {                                    // stream is idle here (we sync every wave)
+                CU(cudaMemsetAsync(sc->ctr_pool.p, 0, kCtrPool * 4, st)); ctr_idx = 0;
+            }
+            uint32_t* ctr = sc->ctr_pool.p + ctr_idx; ctr_idx += 8;          // [0] closest work, [1] shadow work, [2] child count, [3] shadow count, [4] slow count
+            if ((rc = launch_wave(X, d, q_base, n, nullptr, ctr, d + 1 <= L ? counts[d + 1] : 0))) return rc;
+            CU(cudaMemcpyAsync(sc->h_ctr, ctr, 16, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            if (d + 1 <= L) counts[d + 1] += sc->h_ctr[2];
+            X.rays_closest += n; X.rays_shadow += sc->h_ctr[3];
+            X.waves++;
+            if (d + 1 <= L && counts[d + 1] > sc->level_cap) return fail(RTX_E_INVALID, "internal: ray queue overflow");
+            if (sc->h_ctr[3] > sc->shadow_cap) return fail(RTX_E_INVALID, "internal: shadow queue overflow");
+        }
+        resolve_kernel<<<std::min<uint32_t>((pl->n + 255) / 256, gs), 256, 0, st>>>(F, pl->d.p, pl->n, (uchar4*)d_rgba, (float*)d_normals, (float*)d_depth,
+                                                                                (uint32_t*)d_object_ids);
+        X.launches++;
+        CU(cudaEventRecord(X.event(1), st));
+        CU(cudaMemcpyAsync(sc->h_ctr, sc->overflow.p, 16, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
-        if (d + 1 <= L) counts[d + 1] += sc->h_ctr[2];
-        rays_closest += n; rays_shadow += sc->h_ctr[3];
-        waves++;
-        if (d + 1 <= L && counts[d + 1] > sc->level_cap) return fail(RTX_E_INVALID, "internal: ray queue overflow");
-        if (sc->h_ctr[3] > sc->shadow_cap) return fail(RTX_E_INVALID, "internal: shadow queue overflow");
+        CU(cudaGetLastError());
+        memcpy(ovf, sc->h_ctr, 16);
+        if (ovf[0]) return fail(RTX_E_INVALID, "internal: ray queue overflow");
+        break;
     }
-    resolve_kernel<<<std::min<uint32_t>((pl->n + 255) / 256, gs), 256, 0, st>>>(F, pl->d.p, pl->n, (uchar4*)d_rgba, (float*)d_normals, (float*)d_depth,
-                                                                            (uint32_t*)d_object_ids);
-    launches++;
-    CU(cudaEventRecord(get_event(1), st));
-    CU(cudaStreamSynchronize(st));
-    CU(cudaGetLastError());
-    uint32_t ovf[4]; CU(cudaMemcpy(ovf, sc->overflow.p, 16, cudaMemcpyDeviceToHost));
-    if (ovf[0]) return fail(RTX_E_INVALID, "internal: ray queue overflow");
     if (ovf[1]) return fail(RTX_E_INVALID, "internal: traversal stack overflow");
     if (stats) {
         memset(stats, 0, sizeof(*stats));
         float ms = 0.f; cudaEventElapsedTime(&ms, sc->events[0], sc->events[1]);
         float tc = 0.f, ts = 0.f;
-        for (size_t i = 2; i + 3 < ev_next + 0 && i + 3 < sc->events.size(); i += 4) {
+        for (size_t i = 2; i + 3 < X.ev_next + 0 && i + 3 < sc->events.size(); i += 4) {
             float a = 0.f, b = 0.f;
             cudaEventElapsedTime(&a, sc->events[i], sc->events[i + 1]); cudaEventElapsedTime(&b, sc->events[i + 2], sc->events[i + 3]);
             tc += a; ts += b;
         }
         stats->device_ms = ms; stats->closest_ms = tc; stats->shadow_ms = ts; stats->shade_ms = ms - tc - ts;
-        stats->rays_closest = rays_closest; stats->rays_shadow = rays_shadow; stats->primary_samples = primary;
-        stats->kernel_launches = launches; stats->waves = waves; stats->batches = batches;
-        stats->h2d_bytes = h2d; stats->d2h_bytes = (uint64_t)waves * 16;
+        stats->rays_closest = X.rays_closest; stats->rays_shadow = X.rays_shadow; stats->primary_samples = X.primary;
+        stats->kernel_launches = X.launches; stats->waves = X.waves; stats->batches = X.batches;
+        stats->h2d_bytes = h2d; stats->d2h_bytes = sync_free ? (uint64_t)8 * (L + 1) * 4 + 16 : (uint64_t)X.waves * 16 + 16;
         stats->rays_shadow_skipped = ovf[2]; stats->rays_shadow += ovf[2];
-        if (want_stats) {
+        stats->host_syncs = sync_free ? 1u : X.waves + 1u;
+        if (X.want_stats) {
             Counters c; CU(cudaMemcpy(&c, sc->counters.p, sizeof(c), cudaMemcpyDeviceToHost));
             if (getenv("RTX_PHASE_STATS"))
                 for (int k = 0; k < 2; k++) {
@@ -820,22 +936,91 @@ int rtx_render_frame_device(RtxScene* sc, const RtxCamera* cam, const RtxConfig*
     return RTX_OK;
 }
 
-int rtx_render_frame(RtxScene* sc, const RtxCamera* cam, const RtxConfig* cfg, uint8_t* rgba, float* normals, float* depth, uint32_t* object_ids,
-                     RtxStats* stats) {
+void add_stats(RtxStats& a, const RtxStats& b) {
+    a.rays_closest += b.rays_closest; a.rays_shadow += b.rays_shadow; a.primary_samples += b.primary_samples;
+    for (int k = 0; k < 2; k++) { a.node_visits[k] += b.node_visits[k]; a.tri_tests[k] += b.tri_tests[k]; }
+    a.sphere_tests += b.sphere_tests; a.item_tests += b.item_tests; a.kernel_launches += b.kernel_launches;
+    a.waves += b.waves; a.batches += b.batches; a.host_syncs += b.host_syncs;
+    // times: the frame takes as long as its slowest device
+    if (b.device_ms > a.device_ms) { a.device_ms = b.device_ms; a.closest_ms = b.closest_ms; a.shadow_ms = b.shadow_ms; a.shade_ms = b.shade_ms; }
+    a.h2d_bytes += b.h2d_bytes; a.d2h_bytes += b.d2h_bytes; a.rays_shadow_skipped += b.rays_shadow_skipped;
+}
+
+// Frame of a handle: one device, or (rtx_scene_create_multi, shard == NULL) every device its interleaved tiles, all
+// resolving into the SAME output buffers — the caller's, on the first device, written by the others through peer memory.
+int render_frame_any(RtxScene* sc, const RtxCamera* cam, const RtxConfig* cfg, const RtxShard* shard, void* d_rgba, void* d_normals,
+                     void* d_depth, void* d_object_ids, cudaStream_t st, RtxStats* stats) {
+    if (!sc || !cam || !cfg) return fail(RTX_E_INVALID, "null argument");
+    if (cam->width == 0 || cam->height == 0 || (uint64_t)cam->width * cam->height > 0x7fffffffull) return fail(RTX_E_INVALID, "bad frame size");
+    if (cfg->samples == 0 || cfg->samples > 65535) return fail(RTX_E_INVALID, "samples out of range (u16)");
+    if (cfg->max_recursion > 254) return fail(RTX_E_INVALID, "max_recursion > 254 is not supported");
+    if (sc->replicas.empty()) return render_frame_single(sc, cam, cfg, shard, d_rgba, d_normals, d_depth, d_object_ids, st, stats);
+    if (shard) return fail(RTX_E_INVALID, "a multi-device scene shards the frame itself: pass shard = NULL");
+    const uint32_t world = 1 + (uint32_t)sc->replicas.size();
+    CU(cudaSetDevice(sc->device));
+    CU(cudaEventRecord(sc->fence, st));                                   // the replicas start after what the caller queued before this frame
+    std::vector<int> rcs(world, RTX_OK); std::vector<std::string> errs(world); std::vector<RtxStats> sts(world);
+    auto work = [&](uint32_t k) {
+        RtxScene* r = k == 0 ? sc : sc->replicas[k - 1];
+        const RtxShard sh{k, world, 8, 4};
+        cudaStream_t s = st;
+        if (k) {
+            cudaSetDevice(r->device);
+            s = r->own_stream;
+            cudaStreamWaitEvent(s, sc->fence, 0);
+        }
+        rcs[k] = render_frame_single(r, cam, cfg, &sh, d_rgba, d_normals, d_depth, d_object_ids, s, &sts[k]);
+        if (rcs[k]) errs[k] = g_err;
+    };
+    std::vector<std::thread> th;
+    for (uint32_t k = 1; k < world; k++) th.emplace_back(work, k);
+    work(0);
+    for (std::thread& t : th) t.join();
+    CU(cudaSetDevice(sc->device));
+    for (uint32_t k = 0; k < world; k++) if (rcs[k]) return fail(rcs[k], errs[k]);
+    if (stats) { *stats = sts[0]; for (uint32_t k = 1; k < world; k++) add_stats(*stats, sts[k]); }
+    return RTX_OK;
+}
+
+int frame_to_host(RtxScene* sc, const RtxCamera* cam, const RtxConfig* cfg, uint8_t* rgba, float* normals, float* depth, uint32_t* object_ids,
+                  RtxStats* stats) {
     if (!sc || !cam || !cfg) return fail(RTX_E_INVALID, "null argument");
     CU(cudaSetDevice(sc->device));
     const size_t n = (size_t)cam->width * cam->height;
     int rc;
     if ((rc = sc->o_rgba.alloc(n)) || (rc = sc->o_normals.alloc(3 * n)) || (rc = sc->o_depth.alloc(n)) || (rc = sc->o_ids.alloc(n))) return rc;
     RtxStats st;
-    rc = rtx_render_frame_device(sc, cam, cfg, nullptr, sc->o_rgba.p, sc->o_normals.p, sc->o_depth.p, sc->o_ids.p, nullptr, &st);
+    rc = render_frame_any(sc, cam, cfg, nullptr, sc->o_rgba.p, sc->o_normals.p, sc->o_depth.p, sc->o_ids.p, nullptr, &st);
     if (rc) return rc;
-    if (rgba) { CU(cudaMemcpy(rgba, sc->o_rgba.p, n * 4, cudaMemcpyDeviceToHost)); st.d2h_bytes += n * 4; }
-    if (normals) { CU(cudaMemcpy(normals, sc->o_normals.p, n * 12, cudaMemcpyDeviceToHost)); st.d2h_bytes += n * 12; }
-    if (depth) { CU(cudaMemcpy(depth, sc->o_depth.p, n * 4, cudaMemcpyDeviceToHost)); st.d2h_bytes += n * 4; }
-    if (object_ids) { CU(cudaMemcpy(object_ids, sc->o_ids.p, n * 4, cudaMemcpyDeviceToHost)); st.d2h_bytes += n * 4; }
+    // the four copies are queued together and waited for once (page-locked destinations run at full rate; pageable ones are
+    // staged by the driver)
+    if (rgba) { CU(cudaMemcpyAsync(rgba, sc->o_rgba.p, n * 4, cudaMemcpyDeviceToHost, 0)); st.d2h_bytes += n * 4; }
+    if (normals) { CU(cudaMemcpyAsync(normals, sc->o_normals.p, n * 12, cudaMemcpyDeviceToHost, 0)); st.d2h_bytes += n * 12; }
+    if (depth) { CU(cudaMemcpyAsync(depth, sc->o_depth.p, n * 4, cudaMemcpyDeviceToHost, 0)); st.d2h_bytes += n * 4; }
+    if (object_ids) { CU(cudaMemcpyAsync(object_ids, sc->o_ids.p, n * 4, cudaMemcpyDeviceToHost, 0)); st.d2h_bytes += n * 4; }
+    CU(cudaStreamSynchronize(0));
     if (stats) *stats = st;
     return RTX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rtx_render_frame_device(RtxScene* sc, const RtxCamera* cam, const RtxConfig* cfg, const RtxShard* shard, void* d_rgba, void* d_normals,
+                            void* d_depth, void* d_object_ids, void* cuda_stream, RtxStats* stats) {
+    if (!sc) return fail(RTX_E_INVALID, "null argument");
+    if (sc->running.load()) return fail(RTX_E_BUSY, "a frame is in flight on this handle");
+    std::lock_guard<std::mutex> lk(sc->api_mu);
+    return render_frame_any(sc, cam, cfg, shard, d_rgba, d_normals, d_depth, d_object_ids, (cudaStream_t)cuda_stream, stats);
+}
+
+int rtx_render_frame(RtxScene* sc, const RtxCamera* cam, const RtxConfig* cfg, uint8_t* rgba, float* normals, float* depth, uint32_t* object_ids,
+                     RtxStats* stats) {
+    if (!sc) return fail(RTX_E_INVALID, "null argument");
+    if (sc->running.load()) return fail(RTX_E_BUSY, "a frame is in flight on this handle");
+    std::lock_guard<std::mutex> lk(sc->api_mu);
+    return frame_to_host(sc, cam, cfg, rgba, normals, depth, object_ids, stats);
 }
 
 // ---- non-blocking frame (reference src/renderer.rs:105-231) ---------------------------------------------
@@ -849,7 +1034,8 @@ int rtx_render_frame_async(RtxScene* sc, const RtxCamera* cam, const RtxConfig* 
     sc->snap_rgba = rgba; sc->snap_normals = normals; sc->snap_depth = depth; sc->snap_ids = object_ids; sc->snap_req.store(0);
     const RtxCamera c = *cam; const RtxConfig g = *cfg;
     sc->worker = std::thread([=]() {
-        int rc = rtx_render_frame(sc, &c, &g, rgba, normals, depth, object_ids, &sc->async_stats);
+        int rc;
+        { std::lock_guard<std::mutex> lk(sc->api_mu); rc = frame_to_host(sc, &c, &g, rgba, normals, depth, object_ids, &sc->async_stats); }
         sc->async_result = rc;
         if (rc) sc->async_err = g_err;                                    // g_err is thread-local: keep the worker's message
         { std::lock_guard<std::mutex> lk(sc->snap_mu); sc->running.store(false, std::memory_order_release); sc->snap_req.store(0); }
@@ -896,32 +1082,89 @@ int rtx_render_stop(RtxScene* sc) {
 }
 
 // ---- probe ------------------------------------------------------------------------------------------
+}  // extern "C"
+namespace {
+constexpr uint32_t kProbeChunk = 1u << 20;
+// Probes run on their own stream with their own queue / hit / counter buffers: a pick while a frame is in flight (the GUI
+// picks on every click, reference run.rs:1613) touches nothing the frame uses; the scene arrays are read-only for both.
+int probe_prepare(RtxScene* sc, bool shadow) {
+    RtxScene::Probe& P = sc->probe;
+    if (!P.st) CU(cudaStreamCreateWithFlags(&P.st, cudaStreamNonBlocking));
+    const uint32_t cap = kProbeChunk;
+    int rc;
+    if ((rc = P.q_o.alloc(cap)) || (rc = P.q_d.alloc(cap)) || (rc = P.q_m.alloc(cap)) || (rc = P.hits.alloc(cap)) || (rc = P.ctr.alloc(64))) return rc;
+    if (shadow && ((rc = P.s_c.alloc(cap)) || (rc = P.s_r.alloc(cap)) || (rc = P.slow.alloc(cap)) || (rc = P.acc.alloc(cap)) || (rc = P.out.alloc(cap)) ||
+                   (rc = P.len.alloc(cap)) || (rc = P.recv.alloc(cap)) || (rc = P.res.alloc(cap)))) return rc;
+    P.cap = cap;
+    return RTX_OK;
+}
+}  // namespace
+extern "C" {
+
 int rtx_trace_probe(RtxScene* sc, const RtxRay* rays, size_t n, int for_shadow, int stop_on_first_hit, uint32_t depth, RtxHit* hits) {
     if (!sc || (n && (!rays || !hits))) return fail(RTX_E_INVALID, "null argument");
     if (n == 0) return RTX_OK;
     if (n > 0x7fffffffull) return fail(RTX_E_INVALID, "too many rays");
     static_assert(sizeof(ProbeRay) == sizeof(RtxRay) && sizeof(ProbeHit) == sizeof(RtxHit), "probe layouts");
+    std::lock_guard<std::mutex> lk(sc->probe.mu);
     CU(cudaSetDevice(sc->device));
     int rc;
-    if ((rc = sc->p_rays.alloc(n)) || (rc = sc->p_hits.alloc(n))) return rc;
-    CU(cudaMemcpy(sc->p_rays.p, rays, n * sizeof(RtxRay), cudaMemcpyHostToDevice));
+    if ((rc = probe_prepare(sc, false)) || (rc = sc->p_rays.alloc(n)) || (rc = sc->p_hits.alloc(n))) return rc;
+    RtxScene::Probe& P = sc->probe;
+    CU(cudaMemcpyAsync(sc->p_rays.p, rays, n * sizeof(RtxRay), cudaMemcpyHostToDevice, P.st));
     if (!for_shadow && !stop_on_first_hit) {
-        // camera-type rays go through the PRODUCTION kernel (persistent closest_kernel), in chunks of the ray queue
-        if ((rc = ensure_queues(*sc, 6, 1)) || (rc = occupancy_blocks(*sc))) return rc;
-        RayQ Q = level_queue(*sc, 1);
-        for (size_t off = 0; off < n; off += sc->chunk) {
-            const uint32_t m = (uint32_t)std::min<size_t>(sc->chunk, n - off);
-            CU(cudaMemsetAsync(sc->ctr_pool.p, 0, 32, 0));
-            probe_pack_kernel<<<(m + 127) / 128, 128>>>(sc->p_rays.p + off, m, depth, Q);
+        // camera-type rays go through the PRODUCTION kernel (persistent closest_kernel), a chunk at a time
+        RayQ Q{P.q_o.p, P.q_d.p, P.q_m.p};
+        for (size_t off = 0; off < n; off += P.cap) {
+            const uint32_t m = (uint32_t)std::min<size_t>(P.cap, n - off);
+            CU(cudaMemsetAsync(P.ctr.p, 0, 32, P.st));
+            probe_pack_kernel<<<(m + 127) / 128, 128, 0, P.st>>>(sc->p_rays.p + off, m, depth, Q);
             const int blocks = (int)std::min<uint32_t>((m + kTraceBlock - 1) / kTraceBlock, (uint32_t)sc->blocks_closest);
-            closest_kernel<false><<<blocks, kTraceBlock>>>(sc->dev, Q, 0, m, sc->hits.p, sc->ctr_pool.p, sc->counters.p);
-            probe_unpack_kernel<<<(m + 127) / 128, 128>>>(sc->dev, sc->p_rays.p + off, sc->hits.p, m, sc->p_hits.p + off);
+            closest_kernel<false><<<blocks, kTraceBlock, 0, P.st>>>(sc->dev, Q, 0, m, nullptr, P.hits.p, P.ctr.p, nullptr);
+            probe_unpack_kernel<<<(m + 127) / 128, 128, 0, P.st>>>(sc->dev, sc->p_rays.p + off, P.hits.p, m, sc->p_hits.p + off);
         }
     } else {
-        probe_kernel<<<(unsigned)((n + 127) / 128), 128>>>(sc->dev, sc->p_rays.p, (uint32_t)n, for_shadow, stop_on_first_hit, depth, sc->p_hits.p);
+        // trace(.., stop_on_first_hit / for_shadow) returning (t, normal, item, face): the literal reference-order walk.
+        // The production shadow kernels only answer lit / occluded; they are probed by rtx_shadow_probe.
+        probe_kernel<<<(unsigned)((n + 127) / 128), 128, 0, P.st>>>(sc->dev, sc->p_rays.p, (uint32_t)n, for_shadow, stop_on_first_hit, depth, sc->p_hits.p);
     }
     CU(cudaGetLastError());
-    CU(cudaMemcpy(hits, sc->p_hits.p, n * sizeof(RtxHit), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpyAsync(hits, sc->p_hits.p, n * sizeof(RtxHit), cudaMemcpyDeviceToHost, P.st));
+    CU(cudaStreamSynchronize(P.st));
+    return RTX_OK;
+}
+
+int rtx_shadow_probe(RtxScene* sc, const RtxRay* rays, const float* light_distance, const int32_t* receiver_item, size_t n, uint32_t depth,
+                     RtxShadowHit* out) {
+    if (!sc || (n && (!rays || !out))) return fail(RTX_E_INVALID, "null argument");
+    if (n == 0) return RTX_OK;
+    static_assert(sizeof(ShadowProbeOut) == sizeof(RtxShadowHit), "shadow probe layout");
+    if (receiver_item) for (size_t i = 0; i < n; i++) if (receiver_item[i] >= (int32_t)sc->h_items.size()) return fail(RTX_E_INVALID, "receiver item out of range");
+    std::lock_guard<std::mutex> lk(sc->probe.mu);
+    CU(cudaSetDevice(sc->device));
+    int rc;
+    if ((rc = probe_prepare(sc, true))) return rc;
+    RtxScene::Probe& P = sc->probe;
+    if ((rc = sc->p_rays.alloc(P.cap))) return rc;
+    FrameDev F; memset(&F, 0, sizeof(F)); F.accum_c = P.acc.p;
+    ShadowQ SQ{P.q_o.p, P.q_d.p, P.s_c.p, P.s_r.p, P.out.p};
+    ShadowProbeOut* d_out = P.res.p;
+    for (size_t off = 0; off < n; off += P.cap) {
+        const uint32_t m = (uint32_t)std::min<size_t>(P.cap, n - off);
+        CU(cudaMemcpyAsync(sc->p_rays.p, rays + off, (size_t)m * sizeof(RtxRay), cudaMemcpyHostToDevice, P.st));
+        if (light_distance) CU(cudaMemcpyAsync(P.len.p, light_distance + off, (size_t)m * 4, cudaMemcpyHostToDevice, P.st));
+        if (receiver_item) CU(cudaMemcpyAsync(P.recv.p, receiver_item + off, (size_t)m * 4, cudaMemcpyHostToDevice, P.st));
+        CU(cudaMemsetAsync(P.ctr.p, 0, 32, P.st));
+        shadow_probe_pack_kernel<<<(m + 127) / 128, 128, 0, P.st>>>(sc->dev, sc->p_rays.p, light_distance ? P.len.p : nullptr, receiver_item ? P.recv.p : nullptr, m, SQ,
+                                                                  P.acc.p, P.ctr.p + 3);
+        // exactly what a frame launches after its shade kernel (launch_wave)
+        shadow_any_kernel<false><<<sc->blocks_shadow, kTraceBlock, 0, P.st>>>(sc->dev, F, SQ, P.ctr.p + 3, m, depth, P.ctr.p + 1, P.slow.p, P.ctr.p + 4, nullptr);
+        shadow_exact_kernel<false, false><<<sc->sm_count * 8, kTraceBlock, 0, P.st>>>(sc->dev, F, SQ, P.slow.p, P.ctr.p + 4, m, depth, nullptr);
+        shadow_probe_unpack_kernel<<<(m + 127) / 128, 128, 0, P.st>>>(P.acc.p, P.out.p, m, d_out);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(out + off, d_out, (size_t)m * sizeof(RtxShadowHit), cudaMemcpyDeviceToHost, P.st));
+        CU(cudaStreamSynchronize(P.st));
+    }
     return RTX_OK;
 }
 
@@ -990,6 +1233,201 @@ int rtx_shard_unpack(uint32_t w, uint32_t h, const RtxShard* shard, const void* 
                                                                             (const float*)(base + (size_t)n * 16), (const uint32_t*)(base + (size_t)n * 20),
                                                                             (uchar4*)d_rgba, (float*)d_normals, (float*)d_depth, (uint32_t*)d_ids);
     CU(cudaGetLastError());
+    return RTX_OK;
+}
+
+// Scatter the packed shards of ranks first_rank .. world-1 (rank r at d_packed_all + r * stride_bytes) with ONE kernel.
+int rtx_shard_unpack_all(uint32_t w, uint32_t h, uint32_t world, uint32_t tile_w, uint32_t tile_h, uint32_t first_rank, const void* d_packed_all,
+                         uint64_t stride_bytes, void* d_rgba, void* d_normals, void* d_depth, void* d_ids, void* cuda_stream) {
+    if (!d_rgba || !d_normals || !d_depth || !d_ids || !d_packed_all) return fail(RTX_E_INVALID, "null argument");
+    if (world == 0 || first_rank > world || tile_w == 0 || tile_h == 0) return fail(RTX_E_INVALID, "bad shard");
+    struct Entry { uint2* list; uint32_t* start; uint32_t n; };
+    static std::map<std::tuple<int, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t>, Entry> cache;
+    static std::mutex mu;
+    int dev = 0; CU(cudaGetDevice(&dev));
+    Entry en;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto key = std::make_tuple(dev, w, h, world, tile_w, tile_h, first_rank);
+        auto it = cache.find(key);
+        if (it == cache.end()) {
+            std::vector<uint2> list; std::vector<uint32_t> start(2 * world, 0);
+            const uint32_t tx = (w + tile_w - 1) / tile_w, ty = (h + tile_h - 1) / tile_h;
+            for (uint32_t r = 0; r < world; r++) {
+                start[r] = (uint32_t)list.size();
+                uint32_t cnt = 0;
+                const RtxShard sh{r, world, tile_w, tile_h};
+                for_each_owned_tile(sh, tx * ty, [&](uint32_t t) {
+                    const uint32_t x0 = (t % tx) * tile_w, y0 = (t / tx) * tile_h;
+                    for (uint32_t y = y0; y < std::min(y0 + tile_h, h); y++)
+                        for (uint32_t x = x0; x < std::min(x0 + tile_w, w); x++) { if (r >= first_rank) list.push_back(make_uint2(y * w + x, r)); cnt++; }
+                });
+                start[world + r] = cnt;
+            }
+            Entry e{nullptr, nullptr, (uint32_t)list.size()};
+            CU(cudaMalloc(&e.list, std::max<size_t>(1, list.size()) * sizeof(uint2)));
+            CU(cudaMalloc(&e.start, start.size() * 4));
+            if (!list.empty()) CU(cudaMemcpy(e.list, list.data(), list.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(e.start, start.data(), start.size() * 4, cudaMemcpyHostToDevice));
+            it = cache.emplace(key, e).first;
+        }
+        en = it->second;
+    }
+    if (en.n == 0) return RTX_OK;
+    unpack_all_kernel<<<std::min<uint32_t>((en.n + 255) / 256, 148 * 8), 256, 0, (cudaStream_t)cuda_stream>>>(en.list, en.start, world, en.n, (const uint8_t*)d_packed_all,
+                                                                                                         (size_t)stride_bytes, (uchar4*)d_rgba, (float*)d_normals,
+                                                                                                         (float*)d_depth, (uint32_t*)d_ids);
+    CU(cudaGetLastError());
+    return RTX_OK;
+}
+
+// ---- one process, several GPUs ----------------------------------------------------------------------------
+// The reference's seam is ONE RendererManager::start per frame (src/renderer.rs:105-172); a host that owns that call
+// cannot run one process per GPU.  rtx_scene_create_multi builds the scene once on devices[0], copies the flattened
+// arrays device-to-device to the others, and enables peer access so that every device's resolve kernel can store into
+// the frame buffers of devices[0].  All other entry points take the returned handle unchanged.
+int rtx_scene_create_multi(const RtxSceneDesc* d, const int* devices, uint32_t n_devices, RtxScene** out) {
+    if (!d || !out || !devices || n_devices == 0) return fail(RTX_E_INVALID, "null argument");
+    *out = nullptr;
+    int ndev = rtx_device_count();
+    for (uint32_t k = 0; k < n_devices; k++) {
+        if (devices[k] < 0 || devices[k] >= ndev) return fail(ndev ? RTX_E_INVALID : RTX_E_NO_DEVICE, ndev ? "bad device ordinal" : "no CUDA device: librtx_b200 has no CPU fallback");
+        for (uint32_t j = 0; j < k; j++) if (devices[j] == devices[k]) return fail(RTX_E_INVALID, "device listed twice");
+    }
+    RtxScene* sc = nullptr;
+    int rc = rtx_scene_create(d, devices[0], &sc);
+    if (rc) return rc;
+    auto bail = [&](int code, const std::string& m) { rtx_scene_destroy(sc); return fail(code, m); };
+    if (n_devices > 1 && cudaEventCreateWithFlags(&sc->fence, cudaEventDisableTiming) != cudaSuccess) return bail(RTX_E_CUDA, "cudaEventCreate failed");
+    for (uint32_t k = 1; k < n_devices; k++) {
+        const int dev = devices[k];
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, dev, devices[0]) != cudaSuccess || !can) return bail(RTX_E_CUDA, "no peer access between the listed devices");
+        if (cudaSetDevice(dev) != cudaSuccess) return bail(RTX_E_CUDA, "cudaSetDevice failed");
+        cudaError_t e = cudaDeviceEnablePeerAccess(devices[0], 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return bail(RTX_E_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+        cudaGetLastError();
+        RtxScene* r = new RtxScene();
+        sc->replicas.push_back(r);                                        // owned from here on (bail destroys it)
+        r->device = dev; r->primary = sc;
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return bail(RTX_E_CUDA, "cudaGetDeviceProperties failed");
+        r->sm_count = prop.multiProcessorCount;
+        r->src_items = sc->src_items; r->h_items = sc->h_items; r->src_mats = sc->src_mats; r->mesh_root = sc->mesh_root;
+        r->mesh_tri_base = sc->mesh_tri_base; r->mesh_meta = sc->mesh_meta;
+        r->n_blas_nodes = sc->n_blas_nodes; r->n_tris = sc->n_tris; r->tlas_cap = sc->tlas_cap; r->n_tlas_nodes = sc->n_tlas_nodes;
+        r->texture_bytes = sc->texture_bytes; r->build_ms = sc->build_ms; r->n_enabled_lights = sc->n_enabled_lights;
+        const int s0 = devices[0];
+        if ((rc = r->nodes.clone_from(sc->nodes, s0, dev)) || (rc = r->tris.clone_from(sc->tris, s0, dev)) || (rc = r->items.clone_from(sc->items, s0, dev)) ||
+            (rc = r->tlas_prims.clone_from(sc->tlas_prims, s0, dev)) || (rc = r->verts.clone_from(sc->verts, s0, dev)) || (rc = r->idx.clone_from(sc->idx, s0, dev)) ||
+            (rc = r->uvs.clone_from(sc->uvs, s0, dev)) || (rc = r->uv_idx.clone_from(sc->uv_idx, s0, dev)) || (rc = r->nrms.clone_from(sc->nrms, s0, dev)) ||
+            (rc = r->n_idx.clone_from(sc->n_idx, s0, dev)) || (rc = r->mats.clone_from(sc->mats, s0, dev)) || (rc = r->texs.clone_from(sc->texs, s0, dev)) ||
+            (rc = r->texels.clone_from(sc->texels, s0, dev)) || (rc = r->lights.clone_from(sc->lights, s0, dev))) {
+            std::string keep = g_err; rtx_scene_destroy(sc); g_err = keep; return rc;
+        }
+        if (cudaDeviceSynchronize() != cudaSuccess) return bail(RTX_E_CUDA, "scene replication failed");
+        refresh_dev(*r);
+        r->dev.n_lights = sc->dev.n_lights;
+        if ((rc = occupancy_blocks(*r))) { std::string keep = g_err; rtx_scene_destroy(sc); g_err = keep; return rc; }
+        if (cudaStreamCreateWithFlags(&r->own_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(RTX_E_CUDA, "cudaStreamCreate failed");
+    }
+    cudaSetDevice(devices[0]);
+    *out = sc;
+    return RTX_OK;
+}
+
+int rtx_scene_device_count(const RtxScene* sc) { return sc ? 1 + (int)sc->replicas.size() : 0; }
+
+// ---- frame buffers another process can write (CUDA IPC) -----------------------------------------------------
+// One allocation of 24 bytes per pixel on `device`: rgba8[n] | normals f32[3n] | depth f32[n] | object ids u32[n].  The
+// owner exports a 64-byte handle; the other ranks of a multi-process render open it and pass the four pointers as the
+// outputs of rtx_render_frame_device, so their resolve kernels store finished pixels straight into the owner's memory
+// over NVLink: no pack, no collective, no unpack.
+struct RtxGBuffer { int device; uint32_t w, h; uint8_t* base; bool owner; };
+
+int rtx_gbuffer_create(int device, uint32_t w, uint32_t h, RtxGBuffer** out) {
+    if (!out || !w || !h) return fail(RTX_E_INVALID, "bad argument");
+    CU(cudaSetDevice(device));
+    RtxGBuffer* g = new RtxGBuffer{device, w, h, nullptr, true};
+    cudaError_t e = cudaMalloc(&g->base, (size_t)w * h * 24);
+    if (e != cudaSuccess) { delete g; return fail(RTX_E_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+    cudaMemset(g->base, 0, (size_t)w * h * 24);
+    *out = g;
+    return RTX_OK;
+}
+int rtx_gbuffer_export(RtxGBuffer* g, uint8_t handle[64]) {
+    if (!g || !handle || !g->owner) return fail(RTX_E_INVALID, "bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CU(cudaSetDevice(g->device));
+    cudaIpcMemHandle_t hdl; CU(cudaIpcGetMemHandle(&hdl, g->base));
+    memcpy(handle, &hdl, 64);
+    return RTX_OK;
+}
+int rtx_gbuffer_open(int device, uint32_t w, uint32_t h, const uint8_t handle[64], RtxGBuffer** out) {
+    if (!out || !handle || !w || !h) return fail(RTX_E_INVALID, "bad argument");
+    CU(cudaSetDevice(device));
+    cudaIpcMemHandle_t hdl; memcpy(&hdl, handle, 64);
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, hdl, cudaIpcMemLazyEnablePeerAccess));
+    *out = new RtxGBuffer{device, w, h, (uint8_t*)p, false};
+    return RTX_OK;
+}
+int rtx_gbuffer_pointers(const RtxGBuffer* g, void** rgba, void** normals, void** depth, void** ids) {
+    if (!g) return fail(RTX_E_INVALID, "null argument");
+    const size_t n = (size_t)g->w * g->h;
+    if (rgba) *rgba = g->base; if (normals) *normals = g->base + 4 * n; if (depth) *depth = g->base + 16 * n; if (ids) *ids = g->base + 20 * n;
+    return RTX_OK;
+}
+int rtx_gbuffer_download(const RtxGBuffer* g, uint8_t* rgba, float* normals, float* depth, uint32_t* ids, void* cuda_stream) {
+    if (!g) return fail(RTX_E_INVALID, "null argument");
+    CU(cudaSetDevice(g->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t n = (size_t)g->w * g->h;
+    if (rgba) CU(cudaMemcpyAsync(rgba, g->base, 4 * n, cudaMemcpyDeviceToHost, st));
+    if (normals) CU(cudaMemcpyAsync(normals, g->base + 4 * n, 12 * n, cudaMemcpyDeviceToHost, st));
+    if (depth) CU(cudaMemcpyAsync(depth, g->base + 16 * n, 4 * n, cudaMemcpyDeviceToHost, st));
+    if (ids) CU(cudaMemcpyAsync(ids, g->base + 20 * n, 4 * n, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return RTX_OK;
+}
+int rtx_gbuffer_destroy(RtxGBuffer* g) {
+    if (!g) return RTX_OK;
+    cudaSetDevice(g->device);
+    if (g->owner) cudaFree(g->base); else cudaIpcCloseMemHandle(g->base);
+    delete g;
+    return RTX_OK;
+}
+
+// ---- read-bandwidth micro-benchmark (roofline denominator for L2-resident scenes) -----------
+__global__ void __launch_bounds__(256) bw_read_kernel(const uint4* __restrict__ p, size_t n, uint32_t iters, uint4* sink) {
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (uint32_t it = 0; it < iters; it++)
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+            const uint4 v = __ldcg(p + i);                                // L2 (not L1) — what a node fetch that misses L1 sees
+            acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+        }
+    if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x12345678u) *sink = acc;      // keeps the loads alive
+}
+int rtx_bandwidth_probe(int device, uint64_t bytes, uint32_t iters, float* gbytes_per_s) {
+    if (!gbytes_per_s || bytes < 4096 || iters == 0) return fail(RTX_E_INVALID, "bad argument");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, device));
+    uint4* buf = nullptr; uint4* sink = nullptr;
+    const size_t n = bytes / 16;
+    CU(cudaMalloc(&buf, n * 16)); CU(cudaMalloc(&sink, 16));
+    CU(cudaMemset(buf, 1, n * 16));
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int blocks = prop.multiProcessorCount * 8;
+    bw_read_kernel<<<blocks, 256>>>(buf, n, 2, sink);                     // warm the cache
+    cudaEventRecord(e0);
+    bw_read_kernel<<<blocks, 256>>>(buf, n, iters, sink);
+    cudaEventRecord(e1);
+    cudaError_t e = cudaEventSynchronize(e1);
+    float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf); cudaFree(sink);
+    if (e != cudaSuccess) return fail(RTX_E_CUDA, cudaGetErrorString(e));
+    *gbytes_per_s = (float)((double)n * 16.0 * iters / (ms * 1e-3) / 1e9);
     return RTX_OK;
 }
 

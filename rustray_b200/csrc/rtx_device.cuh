@@ -88,7 +88,7 @@ struct FrameDev {
 // ray queue (SoA): o.xyz + weight | d.xyz + pixel | meta (sample:16 depth:8 flags:8, path)
 struct RayQ { float4* o; float4* d; uint2* m; };
 // shadow queue (SoA): o.xyz + light distance | d.xyz + pixel | contribution rgb + receiver alpha | receiver item
-struct ShadowQ { float4* o; float4* d; float4* c; uint32_t* r; };
+struct ShadowQ { float4* o; float4* d; float4* c; uint32_t* r; uint4* probe; };   // probe: nullptr in frames; rtx_shadow_probe reads (lit, occluder item, toi bits, face) per ray
 struct alignas(16) HitRec { float t; uint32_t item; uint32_t prim; uint32_t flags; };   // item = ~0u: miss
 enum : uint32_t { HF_BACK = 1u, HF_INSIDE = 2u, HF_NEGN = 4u };   // HF_NEGN: parry returned -normalize(n) (t < 0 branch)
 enum : uint32_t { RF_ID_OWNER = 1u };

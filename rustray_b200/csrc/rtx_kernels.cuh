@@ -116,8 +116,11 @@ constexpr int kItemBatch = RTX_ITEM_BATCH;
 #endif
 
 template <bool STATS>
-__global__ void __launch_bounds__(kTraceBlock, RTX_MIN_BLOCKS) closest_kernel(SceneDev S, RayQ q, uint32_t q_base, uint32_t n, HitRec* __restrict__ hits,
-                                                              uint32_t* work, Counters* ctr) {
+__global__ void __launch_bounds__(kTraceBlock, RTX_MIN_BLOCKS) closest_kernel(SceneDev S, RayQ q, uint32_t q_base, uint32_t n_host, const uint32_t* __restrict__ n_ptr,
+                                                              HitRec* __restrict__ hits, uint32_t* work, Counters* ctr) {
+    // n_ptr != nullptr: the ray count is whatever the previous level's shade kernel appended (sync-free frames: the host never
+    // reads it), clamped to the queue capacity n_host
+    const uint32_t n = n_ptr ? min(*n_ptr, n_host) : n_host;
     TravStats st{0, 0}; uint32_t n_items = 0, n_sph = 0;
     uint32_t ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint2 stack[kLaneStack];
@@ -205,14 +208,14 @@ __global__ void __launch_bounds__(kTraceBlock, RTX_MIN_BLOCKS) closest_kernel(Sc
 // (directional light and no alpha-textured material in the scene); the others are compacted into `slow` and
 // K3b re-walks them item by item in the reference's bbox-key order (trace_shadow_fast).
 template <bool STATS>
-__global__ void __launch_bounds__(kTraceBlock, RTX_MIN_BLOCKS) shadow_any_kernel(SceneDev S, FrameDev F, ShadowQ q, const uint32_t* __restrict__ n_ptr, uint32_t depth,
+__global__ void __launch_bounds__(kTraceBlock, RTX_MIN_BLOCKS) shadow_any_kernel(SceneDev S, FrameDev F, ShadowQ q, const uint32_t* __restrict__ n_ptr, uint32_t n_cap, uint32_t depth,
                                                                  uint32_t* work, uint32_t* __restrict__ slow, uint32_t* slow_count, Counters* ctr) {
     TravStats st{0, 0}; uint32_t n_items = 0, n_sph = 0;
     uint32_t ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint2 stack[kLaneStack];
     Lane L; bool has = false, exhausted = false, fin = false; uint32_t my = 0;
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t n = *n_ptr;
+    const uint32_t n = min(*n_ptr, n_cap);
     for (;;) {
         // write-back of the rays that ended since the last refill, all at once (the lanes that are about to be refilled)
         {
@@ -229,6 +232,7 @@ __global__ void __launch_bounds__(kTraceBlock, RTX_MIN_BLOCKS) shadow_any_kernel
                     const float4 rc = q.c[my];
                     const float k = occluded ? 1.0f - rc.w : 1.0f;               // raytracing.rs:898,912
                     atomicAdd(&F.accum_c[__float_as_uint(q.d[my].w)], make_float4(rc.x * k, rc.y * k, rc.z * k, 0.0f));
+                    if (q.probe) q.probe[my] = make_uint4(occluded ? 0u : 1u, L.bitem, 0xFFFFFFFFu, 0u);   // rtx_shadow_probe only
                 } else to_slow = true;
             }
             const uint32_t sm = __ballot_sync(kFull, to_slow);
@@ -313,9 +317,9 @@ __global__ void __launch_bounds__(kTraceBlock, RTX_MIN_BLOCKS) shadow_any_kernel
 // "closest hit of every item in order" version on everything, without K3a).
 template <bool STATS, bool ORDERED>
 __global__ void __launch_bounds__(kTraceBlock) shadow_exact_kernel(SceneDev S, FrameDev F, ShadowQ q, const uint32_t* __restrict__ slow,
-                                                                   const uint32_t* __restrict__ n_ptr, uint32_t depth, Counters* ctr) {
+                                                                   const uint32_t* __restrict__ n_ptr, uint32_t n_cap, uint32_t depth, Counters* ctr) {
     TravStats st{0, 0};
-    const uint32_t n = *n_ptr;
+    const uint32_t n = min(*n_ptr, n_cap);
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
         const uint32_t i = slow ? slow[j] : j;
         const float4 ro = q.o[i], rd = q.d[i], rc = q.c[i];
@@ -331,7 +335,7 @@ __global__ void __launch_bounds__(kTraceBlock) shadow_exact_kernel(SceneDev S, F
             trace_shadow_fast<STATS>(S, o, d, depth, len, b, st);
             in_light = b.item == 0xFFFFFFFFu;
         }
-        float k = 1.0f;
+        float k = 1.0f; uint32_t probe_face = 0;
         if (!in_light) {                                                    // :895-913
             float ssa = rc.w;
             const DItem& occ = S.items[b.item];
@@ -342,6 +346,7 @@ __global__ void __launch_bounds__(kTraceBlock) shadow_exact_kernel(SceneDev S, F
                     const uint32_t face = __float_as_uint(__ldg(S.tris + (size_t)b.prim * 3).w);
                     face_id = (b.flags & HF_BACK) ? face + occ.n_faces : face;
                 }
+                probe_face = face_id;
                 const float3 shp = o + d * b.t;
                 float u, v; item_get_uv(S, recv, shp, face_id, u, v);        // receiver's get_uv (sic, :905)
                 float4 tc;
@@ -350,6 +355,7 @@ __global__ void __launch_bounds__(kTraceBlock) shadow_exact_kernel(SceneDev S, F
             k = 1.0f - ssa;
         }
         atomicAdd(&F.accum_c[pixel], make_float4(rc.x * k, rc.y * k, rc.z * k, 0.0f));
+        if (q.probe) q.probe[i] = make_uint4(in_light ? 1u : 0u, b.item, (!in_light && (S.items[b.item].flags & IF_ALPHA_TEX)) ? __float_as_uint(b.t) : 0xFFFFFFFFu, probe_face);
     }
     if (STATS) { atomicAdd(&ctr->node_visits[1], (unsigned long long)st.nodes); atomicAdd(&ctr->tri_tests[1], (unsigned long long)st.tris); }
 }
@@ -365,9 +371,10 @@ struct ShadeOut {
 #ifndef RTX_SHADE_MIN_BLOCKS
 #define RTX_SHADE_MIN_BLOCKS 8
 #endif
-__global__ void __launch_bounds__(kShadeBlock, RTX_SHADE_MIN_BLOCKS) shade_kernel(SceneDev S, FrameDev F, RayQ q, uint32_t q_base, uint32_t n, const HitRec* __restrict__ hits,
-                                                            ShadeOut out) {
+__global__ void __launch_bounds__(kShadeBlock, RTX_SHADE_MIN_BLOCKS) shade_kernel(SceneDev S, FrameDev F, RayQ q, uint32_t q_base, uint32_t n_host, const uint32_t* __restrict__ n_ptr,
+                                                            const HitRec* __restrict__ hits, ShadeOut out) {
     const float PI = 3.14159265358979323846f;
+    const uint32_t n = n_ptr ? min(*n_ptr, n_host) : n_host;
     uint32_t n_enabled = 0;
     for (uint32_t li = 0; li < S.n_lights; li++) n_enabled += S.lights[li].enabled ? 1u : 0u;
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
@@ -663,6 +670,33 @@ __global__ void probe_unpack_kernel(SceneDev S, const ProbeRay* __restrict__ ray
     out[i] = h;
 }
 
+// rtx_shadow_probe: probe rays through the PRODUCTION shadow kernels.  Each ray is a one-pixel "frame" with a unit light
+// contribution, so accum[i].x ends up as the attenuation factor the kernels apply (raytracing.rs:885-914): 1 lit,
+// 1 - receiver alpha [* occluder alpha texel] occluded.
+struct ShadowProbeOut { float k; int32_t lit; int32_t occluder_index; float t; uint32_t face_id; uint32_t reserved[3]; };
+__global__ void shadow_probe_pack_kernel(SceneDev S, const ProbeRay* __restrict__ rays, const float* __restrict__ len, const int32_t* __restrict__ recv,
+                                         uint32_t n, ShadowQ q, float4* __restrict__ acc, uint32_t* count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *count = n;
+    if (i >= n) return;
+    const int32_t r = recv ? recv[i] : -1;
+    const float alpha = r >= 0 ? S.mats[S.items[r].material].alpha : 1.0f;
+    q.o[i] = make_float4(rays[i].o[0], rays[i].o[1], rays[i].o[2], len ? len[i] : 3.402823466e+38f);
+    q.d[i] = make_float4(rays[i].d[0], rays[i].d[1], rays[i].d[2], __uint_as_float(i));
+    q.c[i] = make_float4(1.0f, 1.0f, 1.0f, alpha);
+    q.r[i] = r >= 0 ? (uint32_t)r : 0u;
+    q.probe[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u);
+    acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__global__ void shadow_probe_unpack_kernel(const float4* __restrict__ acc, const uint4* __restrict__ probe, uint32_t n, ShadowProbeOut* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 p = probe[i];
+    ShadowProbeOut o; o.k = acc[i].x; o.lit = (int32_t)p.x; o.occluder_index = p.x == 0u ? (int32_t)p.y : -1;
+    o.t = p.z == 0xFFFFFFFFu ? -1.0f : __uint_as_float(p.z); o.face_id = p.w; o.reserved[0] = o.reserved[1] = o.reserved[2] = 0;
+    out[i] = o;
+}
+
 // debug (RTX_VERIFY=1): recompute every closest hit of a wave with the simple per-thread traversal and record mismatches
 struct VerifyRec { float o[3], d[3]; uint32_t depth, index; float t_prod; uint32_t item_prod, prim_prod; float t_ref; uint32_t item_ref, prim_ref; };
 __global__ void verify_closest_kernel(SceneDev S, RayQ q, uint32_t q_base, uint32_t n, const HitRec* __restrict__ hits, uint32_t* count, VerifyRec* recs, uint32_t cap) {
@@ -701,6 +735,22 @@ __global__ void unpack_kernel(const uint32_t* __restrict__ pixel_list, uint32_t 
         rgba[p] = p_rgba[i];
         normals[3 * (size_t)p] = p_normals[3 * (size_t)i]; normals[3 * (size_t)p + 1] = p_normals[3 * (size_t)i + 1]; normals[3 * (size_t)p + 2] = p_normals[3 * (size_t)i + 2];
         depth[p] = p_depth[i]; ids[p] = p_ids[i];
+    }
+}
+
+// all ranks' packed shards (rank r at packed + r * stride, layout of pack_kernel) -> frame buffers, one launch
+__global__ void unpack_all_kernel(const uint2* __restrict__ list /* (pixel, rank) */, const uint32_t* __restrict__ start /* per rank: first entry, then count */,
+                                  uint32_t world, uint32_t n, const uint8_t* __restrict__ packed, size_t stride,
+                                  uchar4* rgba, float* normals, float* depth, uint32_t* ids) {
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const uint2 e = __ldg(list + j);
+        const uint32_t p = e.x, r = e.y, i = j - __ldg(start + r), nr = __ldg(start + world + r);
+        const uint8_t* base = packed + (size_t)r * stride;
+        rgba[p] = ((const uchar4*)base)[i];
+        const float* pn = (const float*)(base + (size_t)nr * 4);
+        normals[3 * (size_t)p] = pn[3 * (size_t)i]; normals[3 * (size_t)p + 1] = pn[3 * (size_t)i + 1]; normals[3 * (size_t)p + 2] = pn[3 * (size_t)i + 2];
+        depth[p] = ((const float*)(base + (size_t)nr * 16))[i];
+        ids[p] = ((const uint32_t*)(base + (size_t)nr * 20))[i];
     }
 }
 

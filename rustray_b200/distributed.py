@@ -4,10 +4,14 @@ The reference has no distributed path (threads only).  Pixels are
 scene is read-only during a frame, so the path shards with no data-path collective: the flattened
 scene is replicated on every GPU, the row-major tiles of tile_w x tile_h pixels are dealt out in groups of
 `world` (one tile per rank and group, rotated per group so that a rank does not keep the same image columns),
-each rank renders and resolves its own pixels, and ONE gather per frame brings the packed
-24 B/pixel G-buffer (rgba8 | normal 3xf32 | depth f32 | id u32) to rank 0, which scatters it into the
-four frame buffers (`torch.distributed.gather` over NCCL on GPUs; the same host logic runs over gloo
-on CPU in the tests with a numpy pack/unpack).
+and each rank renders and resolves its own pixels.  The finished pixels reach rank 0 in one of two ways:
+
+  * `PeerFrame` (default on one NVLink box): rank 0 owns the 24 B/pixel frame buffers and exports them through CUDA IPC;
+    every rank's resolve kernel STORES its pixels directly into them over NVLink peer memory (resolve and gather are one
+    kernel, csrc/rtx_api.cu rtx_gbuffer_*); a barrier ends the frame.
+  * `ShardedRenderer.gather`: ONE NCCL gather of the packed G-buffer (rgba8 | normal 3xf32 | depth f32 | id u32) into one
+    contiguous buffer on rank 0 and ONE scatter kernel (the same host logic runs over gloo on CPU in the tests with a
+    numpy pack/unpack).
 """
 from __future__ import annotations
 
@@ -82,6 +86,59 @@ def gather_frame_cpu(rank: int, world: int, width: int, height: int, local_frame
     return out
 
 
+class PeerFrame:
+    """Frame buffers on rank 0 that every rank renders into through NVLink peer memory (CUDA IPC handle broadcast once).
+    `pointers()` are the d_rgba / d_normals / d_depth / d_object_ids to pass to RendererManager.render_device together
+    with this rank's shard; `finish()` is the barrier after which rank 0 holds the whole frame."""
+
+    def __init__(self, lib, width: int, height: int, rank: int, world: int, device_index: int, group=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        self.lib, self.w, self.h, self.rank, self.world, self.group = lib, width, height, rank, world, group
+        self._g = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        if rank == 0:
+            _check(lib, lib.rtx_gbuffer_create(device_index, width, height, C.byref(self._g)))
+            _check(lib, lib.rtx_gbuffer_export(self._g, handle))
+        if world > 1:
+            t = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=torch.device("cuda", device_index))
+            dist.broadcast(t, src=0, group=group)
+            if rank != 0:
+                raw = bytes(t.cpu().tolist())
+                C.memmove(handle, raw, 64)
+                _check(lib, lib.rtx_gbuffer_open(device_index, width, height, handle, C.byref(self._g)))
+        p = [C.c_void_p() for _ in range(4)]
+        _check(lib, lib.rtx_gbuffer_pointers(self._g, *[C.byref(x) for x in p]))
+        self.ptrs = [x.value for x in p]
+
+    def pointers(self):
+        return self.ptrs
+
+    def finish(self) -> None:
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+    def download(self, frame, stream_ptr=0) -> None:
+        """rank 0: copy the assembled frame into a renderer.Frame (page-locked host buffers)."""
+        import ctypes as C
+        _check(self.lib, self.lib.rtx_gbuffer_download(self._g, frame.image.ctypes.data, frame.normals.ctypes.data, frame.depth.ctypes.data,
+                                                       frame.objects.ctypes.data, C.c_void_p(stream_ptr)))
+
+    def close(self) -> None:
+        if self._g:
+            self.lib.rtx_gbuffer_destroy(self._g)
+            self._g = None
+
+
+def _check(lib, rc: int) -> None:
+    if rc != 0:
+        from .renderer import RtxError
+        msg = lib.rtx_last_error()
+        raise RtxError("rtx error %d: %s" % (rc, msg.decode() if msg else ""))
+
+
 class ShardedRenderer:
     """One rank of a multi-GPU render.  `rm` is this rank's RendererManager (scene replicated)."""
 
@@ -99,7 +156,9 @@ class ShardedRenderer:
         self.sizes = [int(lib.rtx_shard_packed_bytes(width, height, abi.RtxShard(r, world, tile[0], tile[1]))) for r in range(world)]
         self.pad = (max(self.sizes) + 15) // 16 * 16
         self.send = torch.zeros(self.pad, dtype=torch.uint8, device=self.dev)
-        self.recv = [torch.zeros(self.pad, dtype=torch.uint8, device=self.dev) for _ in range(world)] if rank == 0 else None
+        # one contiguous receive buffer (world x pad): the gather lands in it and ONE kernel scatters all ranks' pixels
+        self.recv_all = torch.zeros(self.pad * world, dtype=torch.uint8, device=self.dev) if rank == 0 else None
+        self.recv = list(self.recv_all.split(self.pad)) if rank == 0 else None
 
     def render_local(self, cam, cfg) -> abi.RtxStats:
         import torch
@@ -119,11 +178,9 @@ class ShardedRenderer:
         if self.world > 1:
             dist.gather(self.send, self.recv, dst=0, group=group)
             if self.rank == 0:
-                for r in range(1, self.world):
-                    sh = abi.RtxShard(r, self.world, self.tile[0], self.tile[1])
-                    rc = lib.rtx_shard_unpack(self.w, self.h, C.byref(sh), self.recv[r].data_ptr(), self.rgba.data_ptr(),
-                                              self.normals.data_ptr(), self.depth.data_ptr(), self.ids.data_ptr(), stream)
-                    self.rm._check(rc)
+                rc = lib.rtx_shard_unpack_all(self.w, self.h, self.world, self.tile[0], self.tile[1], 1, self.recv_all.data_ptr(), self.pad,
+                                              self.rgba.data_ptr(), self.normals.data_ptr(), self.depth.data_ptr(), self.ids.data_ptr(), stream)
+                self.rm._check(rc)
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -42,7 +42,7 @@ def load_library() -> C.CDLL:
                            "(the CUDA library is the product; there is no CPU fallback)" % p)
         _lib = C.CDLL(p)
         abi.bind(_lib, "rtx_")
-        if _lib.rtx_abi_version() != 1:
+        if _lib.rtx_abi_version() != 2:
             raise RtxError("ABI version mismatch")
     return _lib
 
@@ -78,13 +78,20 @@ class Frame:
 class AbiRenderer:
     """Thin object wrapper over any library exporting the rtx ABI under `prefix`."""
 
-    def __init__(self, lib: C.CDLL, prefix: str, flat_scene: abi.FlatScene, device: int = 0):
+    def __init__(self, lib: C.CDLL, prefix: str, flat_scene: abi.FlatScene, device: int = 0, devices=None):
+        """`devices`: list of CUDA ordinals -> one handle that renders every frame on all of them (rtx_scene_create_multi:
+        scene replicated device-to-device, interleaved tiles, peer-memory stores into the first device's frame buffers)."""
         self._lib, self._p = lib, prefix
         self.flat = flat_scene
-        self.device = device
+        self.devices = [int(d) for d in devices] if devices else [int(device)]
+        self.device = self.devices[0]
         self._h = C.c_void_p()
         desc = flat_scene.desc()
-        rc = self._fn("scene_create")(C.byref(desc), int(device), C.byref(self._h))
+        if len(self.devices) > 1:
+            arr = (C.c_int * len(self.devices))(*self.devices)
+            rc = self._fn("scene_create_multi")(C.byref(desc), arr, len(self.devices), C.byref(self._h))
+        else:
+            rc = self._fn("scene_create")(C.byref(desc), self.device, C.byref(self._h))
         self._check(rc)
 
     def _fn(self, name):
@@ -127,6 +134,22 @@ class AbiRenderer:
             self._check(rc)
         return hits
 
+    def shadow_probe(self, origins, dirs, light_distance=None, receiver_item=None, depth=1) -> np.ndarray:
+        """Shadow rays through the production shadow kernels (rtx_shadow_probe): -> abi.SHADOW_HIT_DTYPE records."""
+        o = np.ascontiguousarray(origins, dtype=np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(dirs, dtype=np.float32).reshape(-1, 3)
+        n = o.shape[0]
+        rays = np.zeros(n, dtype=abi.RAY_DTYPE)
+        rays["origin"], rays["dir"] = o, d
+        out = np.zeros(n, dtype=abi.SHADOW_HIT_DTYPE)
+        ld = None if light_distance is None else np.ascontiguousarray(np.broadcast_to(np.asarray(light_distance, dtype=np.float32), (n,)))
+        rv = None if receiver_item is None else np.ascontiguousarray(np.broadcast_to(np.asarray(receiver_item, dtype=np.int32), (n,)))
+        if n:
+            rc = self._fn("shadow_probe")(self._h, rays.ctypes.data, ld.ctypes.data if ld is not None else None,
+                                          rv.ctypes.data if rv is not None else None, n, int(depth), out.ctypes.data)
+            self._check(rc)
+        return out
+
     def update_items(self, updates) -> None:
         """updates: iterable of (item_index, trans 4x4 (row, col), tran_inverse 4x4)."""
         arr = [abi.RtxItemXform(int(i), abi.colmajor16(t), abi.colmajor16(ti)) for i, t, ti in updates]
@@ -157,8 +180,8 @@ def primary_ray(cam: abi.RtxCamera, x: int, y: int):
 class RendererManager(AbiRenderer):
     """B200 stand-in for reference `RendererManager` (src/renderer.rs:19-60)."""
 
-    def __init__(self, width: int, height: int, flat_scene: abi.FlatScene, device: int = 0):
-        super().__init__(load_library(), "rtx_", flat_scene, device)
+    def __init__(self, width: int, height: int, flat_scene: abi.FlatScene, device: int = 0, devices=None):
+        super().__init__(load_library(), "rtx_", flat_scene, device, devices)
         self.width, self.height = width, height
         self.frame = Frame(width, height, pinned=True)
         self._done = False

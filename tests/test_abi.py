@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 17 and set(names) == set(abi.ABI_SYMBOLS)
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.rtx_abi_version() == 1
+    assert lib.rtx_abi_version() == 2
 
 
 def test_struct_layouts_match_the_header(tmp_path):
@@ -36,7 +36,7 @@ def test_struct_layouts_match_the_header(tmp_path):
     structs = {"RtxTexture": abi.RtxTexture, "RtxMaterial": abi.RtxMaterial, "RtxMesh": abi.RtxMesh, "RtxItem": abi.RtxItem,
                "RtxLight": abi.RtxLight, "RtxSceneDesc": abi.RtxSceneDesc, "RtxCamera": abi.RtxCamera, "RtxConfig": abi.RtxConfig,
                "RtxShard": abi.RtxShard, "RtxStats": abi.RtxStats, "RtxRay": abi.RtxRay, "RtxHit": abi.RtxHit,
-               "RtxBvhInfo": abi.RtxBvhInfo, "RtxItemXform": abi.RtxItemXform}
+               "RtxBvhInfo": abi.RtxBvhInfo, "RtxItemXform": abi.RtxItemXform, "RtxShadowHit": abi.RtxShadowHit}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "rtx.h"', "int main(void){"]
     for name, cls in structs.items():
         lines.append('printf("%s %%zu\\n", sizeof(%s));' % (name, name))

@@ -19,7 +19,7 @@ def test_reference_arm_prints_one_contract_line():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and BASE_KEYS <= set(d) and d["value"] > 0 and d["higher_is_better"] is True
-    assert d["metric"].startswith("Mrays/s") and d["unit"] == "Mrays/s" and d["vs_baseline"] is None and d["scaling"] == "weak"
+    assert d["metric"].startswith("Mrays/s") and d["unit"] == "Mrays/s" and d["vs_baseline"] is None and d["scaling"] == "strong"
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "2x2 cell" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
