@@ -178,6 +178,8 @@ typedef struct RtxStats {
     uint64_t rays_shadow_skipped;   /* RTX_OPT_SKIP_ZERO_SHADOW: shadow rays not traced (included in rays_shadow) */
     uint32_t host_syncs;            /* stream synchronisations inside the frame: 1 for a sync-free frame, waves + 1 otherwise */
     uint32_t reserved;
+    uint64_t rays_shadow_exact;     /* shadow rays whose answer could depend on the reference's first-hit order and that were
+                                       re-walked item by item (shadow_exact_kernel); included in rays_shadow */
 } RtxStats;
 
 typedef struct RtxRay { float origin[3]; float dir[3]; } RtxRay;

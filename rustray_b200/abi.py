@@ -80,7 +80,7 @@ class RtxStats(C.Structure):
                 ("waves", C.c_uint32), ("batches", C.c_uint32),
                 ("device_ms", C.c_float), ("closest_ms", C.c_float), ("shadow_ms", C.c_float), ("shade_ms", C.c_float),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("rays_shadow_skipped", C.c_uint64),
-                ("host_syncs", C.c_uint32), ("reserved", C.c_uint32)]
+                ("host_syncs", C.c_uint32), ("reserved", C.c_uint32), ("rays_shadow_exact", C.c_uint64)]
 
     def as_dict(self) -> dict:
         return {k: (list(getattr(self, k)) if hasattr(getattr(self, k), '__len__') else getattr(self, k)) for k, _ in self._fields_}

@@ -343,7 +343,7 @@ int ensure_queues(RtxScene& sc, uint32_t max_recursion, uint32_t n_lights_enable
     if ((rc = sc.q_o.alloc(qn)) || (rc = sc.q_d.alloc(qn)) || (rc = sc.q_m.alloc(qn))) return rc;
     if ((rc = sc.s_o.alloc(sc.shadow_cap)) || (rc = sc.s_d.alloc(sc.shadow_cap)) || (rc = sc.s_c.alloc(sc.shadow_cap)) || (rc = sc.s_r.alloc(sc.shadow_cap)) || (rc = sc.s_slow.alloc(sc.shadow_cap))) return rc;
     if ((rc = sc.hits.alloc(sc.wave_cap)) || (rc = sc.ctr_pool.alloc(kCtrPool)) || (rc = sc.overflow.alloc(4)) || (rc = sc.counters.alloc(1))) return rc;
-    if (!sc.h_ctr) CU(cudaMallocHost(&sc.h_ctr, (4 + 8 * 66) * sizeof(uint32_t)));
+    if (!sc.h_ctr) CU(cudaMallocHost(&sc.h_ctr, (4 + 8 * 66 + 8) * sizeof(uint32_t)));   // [0..3] overflow flags | [4..531] level counters | [532..539] one wave
     return RTX_OK;
 }
 
@@ -658,7 +658,7 @@ struct FrameCtx {
     RtxScene* sc; cudaStream_t st; FrameDev F; PixelList* pl; const RtxConfig* cfg; const RtxCamera* cam;
     void *d_rgba, *d_normals, *d_depth, *d_ids;
     bool want_stats, ordered, primary_single = false; uint32_t L; int gs;
-    uint64_t launches = 0, rays_closest = 0, rays_shadow = 0, primary = 0; uint32_t waves = 0, batches = 0; size_t ev_next = 2;
+    uint64_t launches = 0, rays_closest = 0, rays_shadow = 0, rays_exact = 0, primary = 0; uint32_t waves = 0, batches = 0; size_t ev_next = 2;
     cudaEvent_t event(size_t i) {
         while (sc->events.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); sc->events.push_back(e); }
         return sc->events[i];
@@ -774,7 +774,7 @@ int render_frame_single(RtxScene* sc, const RtxCamera* cam, const RtxConfig* cfg
     uint32_t ovf[4] = {0, 0, 0, 0};
 
     for (int attempt = 0; attempt < 2; attempt++) {
-        X.launches = 0; X.rays_closest = X.rays_shadow = X.primary = 0; X.waves = X.batches = 0; X.ev_next = 2;
+        X.launches = 0; X.rays_closest = X.rays_shadow = X.rays_exact = X.primary = 0; X.waves = X.batches = 0; X.ev_next = 2;
         X.primary_single = sync_free;
         // events: [0] frame start, [1] frame end, then 4 per wave (closest start/end, shadow start/end)
         CU(cudaEventRecord(X.event(0), st));
@@ -804,6 +804,11 @@ int render_frame_single(RtxScene* sc, const RtxCamera* cam, const RtxConfig* cfg
             CU(cudaStreamSynchronize(st));
             CU(cudaGetLastError());
             memcpy(ovf, sc->h_ctr, 16);
+            if (getenv("RTX_TRACE_SCHED")) {
+                fprintf(stderr, "[sched] sync-free frame: primary %u chunk %u wave_cap %u shadow_cap %u overflow %u |", n1, chunk, sc->wave_cap, sc->shadow_cap, ovf[0]);
+                for (uint32_t d = 1; d <= L; d++) fprintf(stderr, " L%u children %u shadow %u exact %u;", d, sc->h_ctr[4 + 8 * d + 2], sc->h_ctr[4 + 8 * d + 3], sc->h_ctr[4 + 8 * d + 4]);
+                fprintf(stderr, "\n");
+            }
             if (ovf[0]) {                                                 // a level outgrew one wave: redo with the synchronised schedule
                 sc->no_sync_free = true; sync_free = false;
                 continue;
@@ -812,7 +817,7 @@ int render_frame_single(RtxScene* sc, const RtxCamera* cam, const RtxConfig* cfg
             for (uint32_t d = 1; d <= L; d++) {
                 const uint32_t* c = sc->h_ctr + 4 + 8 * d;
                 if (d < L) X.rays_closest += c[2];
-                X.rays_shadow += c[3];
+                X.rays_shadow += c[3]; X.rays_exact += c[4];
             }
             break;
         }
@@ -884,10 +889,11 @@ int render_frame_single(RtxScene* sc, const RtxCamera* cam, const RtxConfig* cfg
             }
             uint32_t* ctr = sc->ctr_pool.p + ctr_idx; ctr_idx += 8;          // [0] closest work, [1] shadow work, [2] child count, [3] shadow count, [4] slow count
             if ((rc = launch_wave(X, d, q_base, n, nullptr, ctr, d + 1 <= L ? counts[d + 1] : 0))) return rc;
-            CU(cudaMemcpyAsync(sc->h_ctr, ctr, 16, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(sc->h_ctr + 532, ctr, 32, cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
+            memcpy(sc->h_ctr, sc->h_ctr + 532, 16);
             if (d + 1 <= L) counts[d + 1] += sc->h_ctr[2];
-            X.rays_closest += n; X.rays_shadow += sc->h_ctr[3];
+            X.rays_closest += n; X.rays_shadow += sc->h_ctr[3]; X.rays_exact += sc->h_ctr[536];
             X.waves++;
             if (d + 1 <= L && counts[d + 1] > sc->level_cap) return fail(RTX_E_INVALID, "internal: ray queue overflow");
             if (sc->h_ctr[3] > sc->shadow_cap) return fail(RTX_E_INVALID, "internal: shadow queue overflow");
@@ -917,7 +923,7 @@ int render_frame_single(RtxScene* sc, const RtxCamera* cam, const RtxConfig* cfg
         stats->rays_closest = X.rays_closest; stats->rays_shadow = X.rays_shadow; stats->primary_samples = X.primary;
         stats->kernel_launches = X.launches; stats->waves = X.waves; stats->batches = X.batches;
         stats->h2d_bytes = h2d; stats->d2h_bytes = sync_free ? (uint64_t)8 * (L + 1) * 4 + 16 : (uint64_t)X.waves * 16 + 16;
-        stats->rays_shadow_skipped = ovf[2]; stats->rays_shadow += ovf[2];
+        stats->rays_shadow_skipped = ovf[2]; stats->rays_shadow += ovf[2]; stats->rays_shadow_exact = X.ordered ? 0 : X.rays_exact;
         stats->host_syncs = sync_free ? 1u : X.waves + 1u;
         if (X.want_stats) {
             Counters c; CU(cudaMemcpy(&c, sc->counters.p, sizeof(c), cudaMemcpyDeviceToHost));
@@ -943,7 +949,7 @@ void add_stats(RtxStats& a, const RtxStats& b) {
     a.waves += b.waves; a.batches += b.batches; a.host_syncs += b.host_syncs;
     // times: the frame takes as long as its slowest device
     if (b.device_ms > a.device_ms) { a.device_ms = b.device_ms; a.closest_ms = b.closest_ms; a.shadow_ms = b.shadow_ms; a.shade_ms = b.shade_ms; }
-    a.h2d_bytes += b.h2d_bytes; a.d2h_bytes += b.d2h_bytes; a.rays_shadow_skipped += b.rays_shadow_skipped;
+    a.h2d_bytes += b.h2d_bytes; a.d2h_bytes += b.d2h_bytes; a.rays_shadow_skipped += b.rays_shadow_skipped; a.rays_shadow_exact += b.rays_shadow_exact;
 }
 
 // Frame of a handle: one device, or (rtx_scene_create_multi, shard == NULL) every device its interleaved tiles, all
