@@ -180,6 +180,8 @@ typedef struct RtxStats {
     uint32_t reserved;
     uint64_t rays_shadow_exact;     /* shadow rays whose answer could depend on the reference's first-hit order and that were
                                        re-walked item by item (shadow_exact_kernel); included in rays_shadow */
+    uint64_t rays_shadow_beyond;    /* occluded shadow rays with a finite light distance that were checked for a hit BEHIND the
+                                       light by an item sorting before the occluder (shadow_beyond_kernel, merged BLAS only) */
 } RtxStats;
 
 typedef struct RtxRay { float origin[3]; float dir[3]; } RtxRay;
@@ -210,6 +212,9 @@ typedef struct RtxBvhInfo {
     uint32_t n_nodes, n_triangles, n_items, tlas_nodes;
     uint64_t node_bytes, triangle_bytes, item_bytes, texture_bytes;
     float build_ms;
+    uint32_t grouped_items, grouped_triangles;   /* identity-transform mesh items merged into one world-space BLAS (their triangles
+                                                    are counted twice in n_triangles: the per-mesh BLASes stay for the exact walk) */
+    uint32_t reserved;
 } RtxBvhInfo;
 
 typedef struct RtxScene RtxScene;   /* opaque */

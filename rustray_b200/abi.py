@@ -80,7 +80,7 @@ class RtxStats(C.Structure):
                 ("waves", C.c_uint32), ("batches", C.c_uint32),
                 ("device_ms", C.c_float), ("closest_ms", C.c_float), ("shadow_ms", C.c_float), ("shade_ms", C.c_float),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("rays_shadow_skipped", C.c_uint64),
-                ("host_syncs", C.c_uint32), ("reserved", C.c_uint32), ("rays_shadow_exact", C.c_uint64)]
+                ("host_syncs", C.c_uint32), ("reserved", C.c_uint32), ("rays_shadow_exact", C.c_uint64), ("rays_shadow_beyond", C.c_uint64)]
 
     def as_dict(self) -> dict:
         return {k: (list(getattr(self, k)) if hasattr(getattr(self, k), '__len__') else getattr(self, k)) for k, _ in self._fields_}
@@ -103,7 +103,8 @@ class RtxShadowHit(C.Structure):
 class RtxBvhInfo(C.Structure):
     _fields_ = [("n_nodes", C.c_uint32), ("n_triangles", C.c_uint32), ("n_items", C.c_uint32),
                 ("tlas_nodes", C.c_uint32), ("node_bytes", C.c_uint64), ("triangle_bytes", C.c_uint64),
-                ("item_bytes", C.c_uint64), ("texture_bytes", C.c_uint64), ("build_ms", C.c_float)]
+                ("item_bytes", C.c_uint64), ("texture_bytes", C.c_uint64), ("build_ms", C.c_float),
+                ("grouped_items", C.c_uint32), ("grouped_triangles", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class RtxItemXform(C.Structure):

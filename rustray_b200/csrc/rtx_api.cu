@@ -101,7 +101,9 @@ struct RtxScene {
     uint32_t n_blas_nodes = 0, n_tris = 0, tlas_cap = 0, n_tlas_nodes = 0;
     size_t texture_bytes = 0; float build_ms = 0.f;
     // device scene
-    DevBuf<float4> nodes, tris; DevBuf<DItem> items; DevBuf<uint32_t> tlas_prims;
+    DevBuf<float4> nodes, tris; DevBuf<DItem> items; DevBuf<uint32_t> tlas_prims, fast_prims;
+    uint32_t group_root = 0xFFFFFFFFu, n_fast_nodes = 0, n_group_tris = 0; std::vector<uint32_t> group_items;   // merged world-space BLAS
+    DevBuf<uint4> s_beyond;
     DevBuf<float> verts, uvs, nrms; DevBuf<uint32_t> idx, uv_idx, n_idx;
     DevBuf<DMaterial> mats; DevBuf<DTex> texs; DevBuf<uchar4> texels; DevBuf<DLight> lights;
     SceneDev dev{};
@@ -123,7 +125,7 @@ struct RtxScene {
     struct Probe {
         cudaStream_t st = nullptr; uint32_t cap = 0; std::mutex mu;
         DevBuf<float4> q_o, q_d, s_c, acc; DevBuf<uint2> q_m; DevBuf<uint32_t> s_r, slow, ctr; DevBuf<HitRec> hits; DevBuf<uint4> out;
-        DevBuf<float> len; DevBuf<int32_t> recv; DevBuf<ShadowProbeOut> res;
+        DevBuf<float> len; DevBuf<int32_t> recv; DevBuf<ShadowProbeOut> res; DevBuf<uint4> beyond;
     } probe;
     // single-process multi-GPU: replicas[k] renders shard k+1 of `1 + replicas.size()` (this handle renders shard 0)
     std::vector<RtxScene*> replicas; RtxScene* primary = nullptr; cudaStream_t own_stream = nullptr; cudaEvent_t fence = nullptr;
@@ -216,6 +218,36 @@ int build_tlas(RtxScene& sc, std::vector<float4>& tlas_nodes, std::vector<uint32
     return RTX_OK;
 }
 
+// Fast TLAS of the persistent kernels: every item that is not in the merged BLAS, plus ONE entry (kGroupPrim) for the merged BLAS.
+// Call after build_tlas (which refreshes the items' world boxes).
+int build_tlas_fast(RtxScene& sc, std::vector<float4>& nodes, std::vector<uint32_t>& prims) {
+    std::vector<Aabb3> boxes; std::vector<uint32_t> ids;
+    const float inf = INFINITY;
+    Aabb3 gb = {{inf, inf, inf}, {-inf, -inf, -inf}}; bool have_group = false;
+    for (size_t i = 0; i < sc.h_items.size(); i++) {
+        const DItem& it = sc.h_items[i];
+        const Aabb3 b = {{it.wlo.x, it.wlo.y, it.wlo.z}, {it.whi.x, it.whi.y, it.whi.z}};
+        if (sc.group_root != 0xFFFFFFFFu && (it.flags & IF_GROUPED)) {
+            for (int k = 0; k < 3; k++) { gb.lo[k] = std::min(gb.lo[k], b.lo[k]); gb.hi[k] = std::max(gb.hi[k], b.hi[k]); }
+            have_group = true;
+        } else { boxes.push_back(b); ids.push_back((uint32_t)i); }
+    }
+    if (have_group) { boxes.push_back(gb); ids.push_back(kGroupPrim); }
+    WideBvh bvh; build_wide_bvh(boxes.data(), (uint32_t)boxes.size(), bvh);
+    if (bvh.max_depth > 6) return fail(RTX_E_INVALID, "TLAS too deep for the traversal stack");
+    nodes.clear();
+    append_nodes(nodes, bvh, sc.n_blas_nodes + sc.tlas_cap, 0);
+    prims.resize(bvh.prim_order.size());
+    for (size_t k = 0; k < prims.size(); k++) prims[k] = ids[bvh.prim_order[k]];
+    sc.n_fast_nodes = (uint32_t)bvh.nodes.size();
+    return RTX_OK;
+}
+
+inline bool is_identity16(const float* m) {
+    for (int i = 0; i < 16; i++) if (m[i] != ((i % 5 == 0) ? 1.0f : 0.0f)) return false;
+    return true;
+}
+
 void fill_lights(const RtxLight* l, uint32_t n, std::vector<DLight>& out) {
     out.resize(n);
     for (uint32_t i = 0; i < n; i++) {
@@ -233,6 +265,7 @@ void refresh_dev(RtxScene& sc) {
     D.mats = sc.mats.p; D.texs = sc.texs.p; D.texels = sc.texels.p; D.lights = sc.lights.p;
     D.n_items = (uint32_t)sc.h_items.size();
     D.tlas_root = sc.n_blas_nodes; D.use_tlas = 1u;
+    D.fast_prims = sc.fast_prims.p; D.fast_root = sc.n_blas_nodes + sc.tlas_cap; D.group_root = sc.group_root;
     D.ball_flip_inside = 1u;
     if (!sc.overflow.p) sc.overflow.alloc(4);
     D.dbg = sc.overflow.p + 1;
@@ -342,6 +375,7 @@ int ensure_queues(RtxScene& sc, uint32_t max_recursion, uint32_t n_lights_enable
     int rc;
     if ((rc = sc.q_o.alloc(qn)) || (rc = sc.q_d.alloc(qn)) || (rc = sc.q_m.alloc(qn))) return rc;
     if ((rc = sc.s_o.alloc(sc.shadow_cap)) || (rc = sc.s_d.alloc(sc.shadow_cap)) || (rc = sc.s_c.alloc(sc.shadow_cap)) || (rc = sc.s_r.alloc(sc.shadow_cap)) || (rc = sc.s_slow.alloc(sc.shadow_cap))) return rc;
+    if (sc.group_root != 0xFFFFFFFFu && (rc = sc.s_beyond.alloc(sc.shadow_cap))) return rc;
     if ((rc = sc.hits.alloc(sc.wave_cap)) || (rc = sc.ctr_pool.alloc(kCtrPool)) || (rc = sc.overflow.alloc(4)) || (rc = sc.counters.alloc(1))) return rc;
     if (!sc.h_ctr) CU(cudaMallocHost(&sc.h_ctr, (4 + 8 * 66 + 8) * sizeof(uint32_t)));   // [0..3] overflow flags | [4..531] level counters | [532..539] one wave
     return RTX_OK;
@@ -499,13 +533,66 @@ int rtx_scene_create(const RtxSceneDesc* d, int device, RtxScene** out) {
         }
     }
 
-    // ---- TLAS (only used above kLinearItems; space reserved for updates) ----
-    std::vector<float4> tlas_nodes; std::vector<uint32_t> tlas_prims;
-    sc->tlas_cap = std::max<uint32_t>(8, d->n_items);
-    if (d->n_items > 0) { int rc = build_tlas(*sc, tlas_nodes, tlas_prims); if (rc) { rtx_scene_destroy(sc); return rc; } }
+    // ---- merged world-space BLAS over the mesh items that carry the identity transform (every primitive of a glTF file does:
+    // Scene::load_gltf bakes the node transforms into the vertices, scene.rs:853-891).  Their triangles are ALSO kept in the
+    // per-mesh BLASes: the reference-order walk (K3b) and the probes go item by item.
+    {
+        uint64_t gt = 0; std::vector<uint32_t> cand;
+        for (uint32_t i = 0; i < d->n_items; i++) {
+            const RtxItem& s = d->items[i];
+            if (s.shape == RTX_SHAPE_MESH && is_identity16(s.trans) && is_identity16(s.tran_inverse)) { cand.push_back(i); gt += d->meshes[s.mesh].n_faces; }
+        }
+        uint64_t max_tris = 4000000; if (const char* e = getenv("RTX_GROUP_MAX_TRIS")) max_tris = (uint64_t)atoll(e);
+        if (cand.size() >= 2 && gt <= max_tris && !getenv("RTX_NO_GROUP")) {
+            std::vector<Aabb3> boxes((size_t)gt); std::vector<uint32_t> p_item((size_t)gt), p_face((size_t)gt);
+            size_t k = 0;
+            for (uint32_t i : cand) {
+                const RtxMesh& m = d->meshes[d->items[i].mesh];
+                for (uint32_t f = 0; f < m.n_faces; f++, k++) {
+                    Aabb3& b = boxes[k];
+                    for (int c = 0; c < 3; c++) { b.lo[c] = INFINITY; b.hi[c] = -INFINITY; }
+                    for (int c = 0; c < 3; c++) {
+                        const float* v = m.vertices + 3 * (size_t)m.indices[3 * (size_t)f + c];
+                        for (int q = 0; q < 3; q++) { b.lo[q] = std::min(b.lo[q], v[q]); b.hi[q] = std::max(b.hi[q], v[q]); }
+                    }
+                    p_item[k] = i; p_face[k] = f;
+                }
+            }
+            WideBvh bvh; build_wide_bvh(boxes.data(), (uint32_t)gt, bvh);
+            if (!(bvh.max_depth >= kStack - 2 || 2 * bvh.max_depth + 2 * 6 + 4 > kLaneStack)) {       // too deep: keep the per-item structure only
+                const uint32_t node_off = (uint32_t)(h_nodes.size() / 5), tri_off = (uint32_t)(h_tris.size() / 3);
+                append_nodes(h_nodes, bvh, node_off, tri_off);
+                for (uint32_t pi : bvh.prim_order) {
+                    const RtxMesh& m = d->meshes[d->items[p_item[pi]].mesh]; const uint32_t f = p_face[pi];
+                    const float* a = m.vertices + 3 * (size_t)m.indices[3 * (size_t)f];
+                    const float* b = m.vertices + 3 * (size_t)m.indices[3 * (size_t)f + 1];
+                    const float* c = m.vertices + 3 * (size_t)m.indices[3 * (size_t)f + 2];
+                    float fb, ib; memcpy(&fb, &f, 4); memcpy(&ib, &p_item[pi], 4);
+                    h_tris.push_back(make_float4(a[0], a[1], a[2], fb));
+                    h_tris.push_back(make_float4(b[0], b[1], b[2], ib));            // .w = item: what the reference does per item happens per accepted triangle
+                    h_tris.push_back(make_float4(c[0], c[1], c[2], 0.f));
+                }
+                sc->group_root = node_off; sc->group_items = cand; sc->n_group_tris = (uint32_t)gt;
+                for (uint32_t i : cand) sc->h_items[i].flags |= IF_GROUPED;
+                sc->n_blas_nodes = (uint32_t)(h_nodes.size() / 5); sc->n_tris = (uint32_t)(h_tris.size() / 3);
+            }
+        }
+    }
+
+    // ---- TLASes: the full one (every item) and the fast one (ungrouped items + the merged BLAS); space reserved for updates ----
+    std::vector<float4> tlas_nodes, fast_nodes; std::vector<uint32_t> tlas_prims, fast_prims;
+    sc->tlas_cap = std::max<uint32_t>(8, d->n_items + 1);
+    if (d->n_items > 0) {
+        int rc = build_tlas(*sc, tlas_nodes, tlas_prims);
+        if (!rc) rc = build_tlas_fast(*sc, fast_nodes, fast_prims);
+        if (rc) { rtx_scene_destroy(sc); return rc; }
+    }
     h_nodes.insert(h_nodes.end(), tlas_nodes.begin(), tlas_nodes.end());
     h_nodes.resize(((size_t)sc->n_blas_nodes + sc->tlas_cap) * 5, make_float4(0, 0, 0, 0));
+    h_nodes.insert(h_nodes.end(), fast_nodes.begin(), fast_nodes.end());
+    h_nodes.resize(((size_t)sc->n_blas_nodes + 2 * (size_t)sc->tlas_cap) * 5, make_float4(0, 0, 0, 0));
     tlas_prims.resize(std::max<size_t>(1, d->n_items), 0);
+    fast_prims.resize(std::max<size_t>(1, (size_t)d->n_items + 1), 0);
 
     // ---- materials / textures / lights ----
     std::vector<DTex> h_texs(d->n_textures); std::vector<uchar4> h_texels;
@@ -537,7 +624,7 @@ int rtx_scene_create(const RtxSceneDesc* d, int device, RtxScene** out) {
     // ---- upload ----
     int rc;
     if ((rc = sc->nodes.upload(h_nodes)) || (rc = sc->tris.upload(h_tris)) || (rc = sc->items.upload(sc->h_items)) ||
-        (rc = sc->tlas_prims.upload(tlas_prims)) || (rc = sc->verts.upload(h_verts)) || (rc = sc->idx.upload(h_idx)) ||
+        (rc = sc->tlas_prims.upload(tlas_prims)) || (rc = sc->fast_prims.upload(fast_prims)) || (rc = sc->verts.upload(h_verts)) || (rc = sc->idx.upload(h_idx)) ||
         (rc = sc->uvs.upload(h_uvs)) || (rc = sc->uv_idx.upload(h_uvidx)) || (rc = sc->nrms.upload(h_nrms)) || (rc = sc->n_idx.upload(h_nidx)) ||
         (rc = sc->mats.upload(h_mats)) || (rc = sc->texs.upload(h_texs)) || (rc = sc->texels.upload(h_texels)) || (rc = sc->lights.upload(h_lights))) {
         std::string keep = g_err; rtx_scene_destroy(sc); g_err = keep; return rc;
@@ -564,12 +651,12 @@ int rtx_scene_destroy(RtxScene* sc) {
     {
         RtxScene::Probe& P = sc->probe;
         P.q_o.release(); P.q_d.release(); P.s_c.release(); P.acc.release(); P.q_m.release(); P.s_r.release(); P.slow.release(); P.ctr.release();
-        P.hits.release(); P.out.release(); P.len.release(); P.recv.release(); P.res.release();
+        P.hits.release(); P.out.release(); P.len.release(); P.recv.release(); P.res.release(); P.beyond.release();
         if (P.st) cudaStreamDestroy(P.st);
     }
     if (sc->own_stream) cudaStreamDestroy(sc->own_stream);
     if (sc->fence) cudaEventDestroy(sc->fence);
-    sc->nodes.release(); sc->tris.release(); sc->items.release(); sc->tlas_prims.release();
+    sc->nodes.release(); sc->tris.release(); sc->items.release(); sc->tlas_prims.release(); sc->fast_prims.release(); sc->s_beyond.release();
     sc->verts.release(); sc->uvs.release(); sc->nrms.release(); sc->idx.release(); sc->uv_idx.release(); sc->n_idx.release();
     sc->mats.release(); sc->texs.release(); sc->texels.release(); sc->lights.release();
     sc->accum_c.release(); sc->accum_n.release(); sc->ids.release(); sc->sample_table.release();
@@ -611,12 +698,26 @@ int rtx_scene_update_items(RtxScene* sc, const RtxItemXform* x, size_t n) {
         d.flags = (t[15] != 1.0f) ? (d.flags | IF_DIV_W) : (d.flags & ~IF_DIV_W);
     }
     CU(cudaDeviceSynchronize());
+    if (sc->group_root != 0xFFFFFFFFu) {
+        // an item of the merged BLAS that is moved leaves world space == object space: the group is dissolved (its items are
+        // walked one by one again, like every other item); a static glTF scene never gets here
+        bool intact = true;
+        for (uint32_t gi : sc->group_items) if (!is_identity16(sc->src_items[gi].trans) || !is_identity16(sc->src_items[gi].tran_inverse)) intact = false;
+        if (!intact) {
+            for (uint32_t gi : sc->group_items) sc->h_items[gi].flags &= ~IF_GROUPED;
+            sc->group_root = 0xFFFFFFFFu; sc->group_items.clear();
+            refresh_dev(*sc);
+        }
+    }
     if (!sc->h_items.empty()) {                                           // Scene::update rebuilds the item BVH (scene.rs:1681-1687)
-        std::vector<float4> tn; std::vector<uint32_t> tp;
+        std::vector<float4> tn, fn; std::vector<uint32_t> tp, fp;
         int rc = build_tlas(*sc, tn, tp); if (rc) return rc;              // also refreshes the items' world boxes
-        if (tn.size() / 5 > sc->tlas_cap) return fail(RTX_E_INVALID, "TLAS capacity exceeded");
+        if ((rc = build_tlas_fast(*sc, fn, fp))) return rc;
+        if (tn.size() / 5 > sc->tlas_cap || fn.size() / 5 > sc->tlas_cap) return fail(RTX_E_INVALID, "TLAS capacity exceeded");
         CU(cudaMemcpy(sc->nodes.p + (size_t)sc->n_blas_nodes * 5, tn.data(), tn.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(sc->nodes.p + ((size_t)sc->n_blas_nodes + sc->tlas_cap) * 5, fn.data(), fn.size() * sizeof(float4), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(sc->tlas_prims.p, tp.data(), tp.size() * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(sc->fast_prims.p, fp.data(), fp.size() * 4, cudaMemcpyHostToDevice));
     }
     CU(cudaMemcpy(sc->items.p, sc->h_items.data(), sc->h_items.size() * sizeof(DItem), cudaMemcpyHostToDevice));
     return RTX_OK;
@@ -643,7 +744,8 @@ int rtx_scene_set_lights(RtxScene* sc, const RtxLight* l, uint32_t n) {
 int rtx_scene_bvh_info(const RtxScene* sc, RtxBvhInfo* info) {
     if (!sc || !info) return fail(RTX_E_INVALID, "null argument");
     info->n_nodes = sc->n_blas_nodes; info->n_triangles = sc->n_tris; info->n_items = (uint32_t)sc->h_items.size();
-    info->tlas_nodes = sc->n_tlas_nodes; info->node_bytes = (uint64_t)(sc->n_blas_nodes + sc->n_tlas_nodes) * 80;
+    info->tlas_nodes = sc->n_tlas_nodes; info->node_bytes = (uint64_t)(sc->n_blas_nodes + sc->n_tlas_nodes + sc->n_fast_nodes) * 80;
+    info->grouped_items = (uint32_t)sc->group_items.size(); info->grouped_triangles = sc->n_group_tris;
     info->triangle_bytes = (uint64_t)sc->n_tris * 48; info->item_bytes = sc->h_items.size() * sizeof(DItem);
     info->texture_bytes = sc->texture_bytes; info->build_ms = sc->build_ms;
     return RTX_OK;
@@ -658,7 +760,7 @@ struct FrameCtx {
     RtxScene* sc; cudaStream_t st; FrameDev F; PixelList* pl; const RtxConfig* cfg; const RtxCamera* cam;
     void *d_rgba, *d_normals, *d_depth, *d_ids;
     bool want_stats, ordered, primary_single = false; uint32_t L; int gs;
-    uint64_t launches = 0, rays_closest = 0, rays_shadow = 0, rays_exact = 0, primary = 0; uint32_t waves = 0, batches = 0; size_t ev_next = 2;
+    uint64_t launches = 0, rays_closest = 0, rays_shadow = 0, rays_exact = 0, rays_beyond = 0, primary = 0; uint32_t waves = 0, batches = 0; size_t ev_next = 2;
     cudaEvent_t event(size_t i) {
         while (sc->events.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); sc->events.push_back(e); }
         return sc->events[i];
@@ -670,7 +772,7 @@ struct FrameCtx {
 int launch_wave(FrameCtx& X, uint32_t d, uint32_t q_base, uint32_t n, const uint32_t* n_ptr, uint32_t* ctr, uint32_t child_off) {
     RtxScene* sc = X.sc; cudaStream_t st = X.st;
     RayQ Q = level_queue(*sc, d);
-    ShadowQ SQ{sc->s_o.p, sc->s_d.p, sc->s_c.p, sc->s_r.p, nullptr};
+    ShadowQ SQ{sc->s_o.p, sc->s_d.p, sc->s_c.p, sc->s_r.p, nullptr, sc->s_beyond.p};
     cudaEvent_t e0 = X.event(X.ev_next), e1 = X.event(X.ev_next + 1), e2 = X.event(X.ev_next + 2), e3 = X.event(X.ev_next + 3);
     X.ev_next += 4;
     const bool verify = !n_ptr && getenv("RTX_VERIFY");
@@ -725,6 +827,11 @@ int launch_wave(FrameCtx& X, uint32_t d, uint32_t q_base, uint32_t n, const uint
         } else {
             if (X.want_stats) shadow_any_kernel<true><<<sc->blocks_shadow_st, kTraceBlock, 0, st>>>(sc->dev, X.F, SQ, ctr + 3, sc->shadow_cap, d, ctr + 1, sc->s_slow.p, ctr + 4, sc->counters.p);
             else shadow_any_kernel<false><<<sc->blocks_shadow, kTraceBlock, 0, st>>>(sc->dev, X.F, SQ, ctr + 3, sc->shadow_cap, d, ctr + 1, sc->s_slow.p, ctr + 4, sc->counters.p);
+            if (sc->dev.group_root != 0xFFFFFFFFu) {
+                if (X.want_stats) shadow_beyond_kernel<true><<<eb, kTraceBlock, 0, st>>>(sc->dev, X.F, SQ, ctr + 5, sc->shadow_cap, d, sc->s_slow.p, ctr + 4, sc->counters.p);
+                else shadow_beyond_kernel<false><<<eb, kTraceBlock, 0, st>>>(sc->dev, X.F, SQ, ctr + 5, sc->shadow_cap, d, sc->s_slow.p, ctr + 4, sc->counters.p);
+                X.launches++;
+            }
             if (X.want_stats) shadow_exact_kernel<true, false><<<eb, kTraceBlock, 0, st>>>(sc->dev, X.F, SQ, sc->s_slow.p, ctr + 4, sc->shadow_cap, d, sc->counters.p);
             else shadow_exact_kernel<false, false><<<eb, kTraceBlock, 0, st>>>(sc->dev, X.F, SQ, sc->s_slow.p, ctr + 4, sc->shadow_cap, d, sc->counters.p);
             X.launches += 2;
@@ -774,7 +881,7 @@ int render_frame_single(RtxScene* sc, const RtxCamera* cam, const RtxConfig* cfg
     uint32_t ovf[4] = {0, 0, 0, 0};
 
     for (int attempt = 0; attempt < 2; attempt++) {
-        X.launches = 0; X.rays_closest = X.rays_shadow = X.rays_exact = X.primary = 0; X.waves = X.batches = 0; X.ev_next = 2;
+        X.launches = 0; X.rays_closest = X.rays_shadow = X.rays_exact = X.rays_beyond = X.primary = 0; X.waves = X.batches = 0; X.ev_next = 2;
         X.primary_single = sync_free;
         // events: [0] frame start, [1] frame end, then 4 per wave (closest start/end, shadow start/end)
         CU(cudaEventRecord(X.event(0), st));
@@ -817,7 +924,7 @@ int render_frame_single(RtxScene* sc, const RtxCamera* cam, const RtxConfig* cfg
             for (uint32_t d = 1; d <= L; d++) {
                 const uint32_t* c = sc->h_ctr + 4 + 8 * d;
                 if (d < L) X.rays_closest += c[2];
-                X.rays_shadow += c[3]; X.rays_exact += c[4];
+                X.rays_shadow += c[3]; X.rays_exact += c[4]; X.rays_beyond += c[5];
             }
             break;
         }
@@ -893,7 +1000,7 @@ int render_frame_single(RtxScene* sc, const RtxCamera* cam, const RtxConfig* cfg
             CU(cudaStreamSynchronize(st));
             memcpy(sc->h_ctr, sc->h_ctr + 532, 16);
             if (d + 1 <= L) counts[d + 1] += sc->h_ctr[2];
-            X.rays_closest += n; X.rays_shadow += sc->h_ctr[3]; X.rays_exact += sc->h_ctr[536];
+            X.rays_closest += n; X.rays_shadow += sc->h_ctr[3]; X.rays_exact += sc->h_ctr[536]; X.rays_beyond += sc->h_ctr[537];
             X.waves++;
             if (d + 1 <= L && counts[d + 1] > sc->level_cap) return fail(RTX_E_INVALID, "internal: ray queue overflow");
             if (sc->h_ctr[3] > sc->shadow_cap) return fail(RTX_E_INVALID, "internal: shadow queue overflow");
@@ -923,7 +1030,7 @@ int render_frame_single(RtxScene* sc, const RtxCamera* cam, const RtxConfig* cfg
         stats->rays_closest = X.rays_closest; stats->rays_shadow = X.rays_shadow; stats->primary_samples = X.primary;
         stats->kernel_launches = X.launches; stats->waves = X.waves; stats->batches = X.batches;
         stats->h2d_bytes = h2d; stats->d2h_bytes = sync_free ? (uint64_t)8 * (L + 1) * 4 + 16 : (uint64_t)X.waves * 16 + 16;
-        stats->rays_shadow_skipped = ovf[2]; stats->rays_shadow += ovf[2]; stats->rays_shadow_exact = X.ordered ? 0 : X.rays_exact;
+        stats->rays_shadow_skipped = ovf[2]; stats->rays_shadow += ovf[2]; stats->rays_shadow_exact = X.ordered ? 0 : X.rays_exact; stats->rays_shadow_beyond = X.ordered ? 0 : X.rays_beyond;
         stats->host_syncs = sync_free ? 1u : X.waves + 1u;
         if (X.want_stats) {
             Counters c; CU(cudaMemcpy(&c, sc->counters.p, sizeof(c), cudaMemcpyDeviceToHost));
@@ -949,7 +1056,7 @@ void add_stats(RtxStats& a, const RtxStats& b) {
     a.waves += b.waves; a.batches += b.batches; a.host_syncs += b.host_syncs;
     // times: the frame takes as long as its slowest device
     if (b.device_ms > a.device_ms) { a.device_ms = b.device_ms; a.closest_ms = b.closest_ms; a.shadow_ms = b.shadow_ms; a.shade_ms = b.shade_ms; }
-    a.h2d_bytes += b.h2d_bytes; a.d2h_bytes += b.d2h_bytes; a.rays_shadow_skipped += b.rays_shadow_skipped; a.rays_shadow_exact += b.rays_shadow_exact;
+    a.h2d_bytes += b.h2d_bytes; a.d2h_bytes += b.d2h_bytes; a.rays_shadow_skipped += b.rays_shadow_skipped; a.rays_shadow_exact += b.rays_shadow_exact; a.rays_shadow_beyond += b.rays_shadow_beyond;
 }
 
 // Frame of a handle: one device, or (rtx_scene_create_multi, shard == NULL) every device its interleaved tiles, all
@@ -1100,7 +1207,7 @@ int probe_prepare(RtxScene* sc, bool shadow) {
     int rc;
     if ((rc = P.q_o.alloc(cap)) || (rc = P.q_d.alloc(cap)) || (rc = P.q_m.alloc(cap)) || (rc = P.hits.alloc(cap)) || (rc = P.ctr.alloc(64))) return rc;
     if (shadow && ((rc = P.s_c.alloc(cap)) || (rc = P.s_r.alloc(cap)) || (rc = P.slow.alloc(cap)) || (rc = P.acc.alloc(cap)) || (rc = P.out.alloc(cap)) ||
-                   (rc = P.len.alloc(cap)) || (rc = P.recv.alloc(cap)) || (rc = P.res.alloc(cap)))) return rc;
+                   (rc = P.len.alloc(cap)) || (rc = P.recv.alloc(cap)) || (rc = P.res.alloc(cap)) || (rc = P.beyond.alloc(cap)))) return rc;
     P.cap = cap;
     return RTX_OK;
 }
@@ -1153,7 +1260,7 @@ int rtx_shadow_probe(RtxScene* sc, const RtxRay* rays, const float* light_distan
     RtxScene::Probe& P = sc->probe;
     if ((rc = sc->p_rays.alloc(P.cap))) return rc;
     FrameDev F; memset(&F, 0, sizeof(F)); F.accum_c = P.acc.p;
-    ShadowQ SQ{P.q_o.p, P.q_d.p, P.s_c.p, P.s_r.p, P.out.p};
+    ShadowQ SQ{P.q_o.p, P.q_d.p, P.s_c.p, P.s_r.p, P.out.p, P.beyond.p};
     ShadowProbeOut* d_out = P.res.p;
     for (size_t off = 0; off < n; off += P.cap) {
         const uint32_t m = (uint32_t)std::min<size_t>(P.cap, n - off);
@@ -1165,6 +1272,8 @@ int rtx_shadow_probe(RtxScene* sc, const RtxRay* rays, const float* light_distan
                                                                   P.acc.p, P.ctr.p + 3);
         // exactly what a frame launches after its shade kernel (launch_wave)
         shadow_any_kernel<false><<<sc->blocks_shadow, kTraceBlock, 0, P.st>>>(sc->dev, F, SQ, P.ctr.p + 3, m, depth, P.ctr.p + 1, P.slow.p, P.ctr.p + 4, nullptr);
+        if (sc->dev.group_root != 0xFFFFFFFFu)
+            shadow_beyond_kernel<false><<<sc->sm_count * 8, kTraceBlock, 0, P.st>>>(sc->dev, F, SQ, P.ctr.p + 5, m, depth, P.slow.p, P.ctr.p + 4, nullptr);
         shadow_exact_kernel<false, false><<<sc->sm_count * 8, kTraceBlock, 0, P.st>>>(sc->dev, F, SQ, P.slow.p, P.ctr.p + 4, m, depth, nullptr);
         shadow_probe_unpack_kernel<<<(m + 127) / 128, 128, 0, P.st>>>(P.acc.p, P.out.p, m, d_out);
         CU(cudaGetLastError());
@@ -1323,9 +1432,10 @@ int rtx_scene_create_multi(const RtxSceneDesc* d, const int* devices, uint32_t n
         r->mesh_tri_base = sc->mesh_tri_base; r->mesh_meta = sc->mesh_meta;
         r->n_blas_nodes = sc->n_blas_nodes; r->n_tris = sc->n_tris; r->tlas_cap = sc->tlas_cap; r->n_tlas_nodes = sc->n_tlas_nodes;
         r->texture_bytes = sc->texture_bytes; r->build_ms = sc->build_ms; r->n_enabled_lights = sc->n_enabled_lights;
+        r->group_root = sc->group_root; r->group_items = sc->group_items; r->n_group_tris = sc->n_group_tris; r->n_fast_nodes = sc->n_fast_nodes;
         const int s0 = devices[0];
         if ((rc = r->nodes.clone_from(sc->nodes, s0, dev)) || (rc = r->tris.clone_from(sc->tris, s0, dev)) || (rc = r->items.clone_from(sc->items, s0, dev)) ||
-            (rc = r->tlas_prims.clone_from(sc->tlas_prims, s0, dev)) || (rc = r->verts.clone_from(sc->verts, s0, dev)) || (rc = r->idx.clone_from(sc->idx, s0, dev)) ||
+            (rc = r->tlas_prims.clone_from(sc->tlas_prims, s0, dev)) || (rc = r->fast_prims.clone_from(sc->fast_prims, s0, dev)) || (rc = r->verts.clone_from(sc->verts, s0, dev)) || (rc = r->idx.clone_from(sc->idx, s0, dev)) ||
             (rc = r->uvs.clone_from(sc->uvs, s0, dev)) || (rc = r->uv_idx.clone_from(sc->uv_idx, s0, dev)) || (rc = r->nrms.clone_from(sc->nrms, s0, dev)) ||
             (rc = r->n_idx.clone_from(sc->n_idx, s0, dev)) || (rc = r->mats.clone_from(sc->mats, s0, dev)) || (rc = r->texs.clone_from(sc->texs, s0, dev)) ||
             (rc = r->texels.clone_from(sc->texels, s0, dev)) || (rc = r->lights.clone_from(sc->lights, s0, dev))) {

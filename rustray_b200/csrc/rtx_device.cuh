@@ -33,8 +33,10 @@ enum : uint32_t {
     IF_SMOOTH = 64u, IF_HAS_NORMALS = 128u, IF_ALPHA_TEX = 256u, IF_ALPHA_POS = 512u, IF_ALPHA_LT1 = 1024u,
     IF_DIV_W = 4096u,          // tran_inverse[3][3] != 1 (rounding of the cofactor inverse): points are divided by it, like from_homogeneous
     IF_TRANSLATION = 2048u,    // tran_inverse is identity + translation: o' = o + t, d' = d (bit-identical to the general product)
-    IF_DIRECT_TRIS = 8192u     // mesh of <= kDirectTris triangles (quads, planes): entering the item queues its triangles, no BLAS node visit
+    IF_DIRECT_TRIS = 8192u,    // mesh of <= kDirectTris triangles (quads, planes): entering the item queues its triangles, no BLAS node visit
+    IF_GROUPED = 16384u        // mesh item with an identity transform whose triangles are (also) in the merged world-space BLAS
 };
+constexpr uint32_t kGroupPrim = 0xFFFFFFFFu;   // entry of the fast TLAS's primitive list that stands for the merged BLAS
 constexpr uint32_t kDirectTris = 4;
 
 struct alignas(16) DItem {
@@ -64,11 +66,13 @@ struct alignas(16) DLight { float pos[3]; uint32_t type; float dir[3]; float int
 
 struct SceneDev {
     const float4* nodes; const float4* tris; const DItem* items;
-    const uint32_t* tlas_prims;
+    const uint32_t* tlas_prims;       // FULL item TLAS (every item; one BLAS per mesh): reference-order walks (K3b), probes, RTX_VERIFY
+    const uint32_t* fast_prims;       // fast TLAS of the persistent kernels: items that are not grouped + kGroupPrim
     const float* verts; const uint32_t* idx; const float* uvs; const uint32_t* uv_idx; const float* nrms; const uint32_t* n_idx;
     const DMaterial* mats; const DTex* texs; const uchar4* texels; const DLight* lights;
     uint32_t n_items, n_lights, tlas_root, use_tlas;
     uint32_t ball_flip_inside, any_alpha_tex, flat_items /* bit mask of tlas_prims entries when n_items <= 24, else 0 */, pad;
+    uint32_t fast_root, group_root /* root of the merged BLAS, ~0u: no group */, pad1, pad2;
     uint32_t* dbg;      // debug counters: [0] lane stack overflow
 };
 
@@ -88,7 +92,7 @@ struct FrameDev {
 // ray queue (SoA): o.xyz + weight | d.xyz + pixel | meta (sample:16 depth:8 flags:8, path)
 struct RayQ { float4* o; float4* d; uint2* m; };
 // shadow queue (SoA): o.xyz + light distance | d.xyz + pixel | contribution rgb + receiver alpha | receiver item
-struct ShadowQ { float4* o; float4* d; float4* c; uint32_t* r; uint4* probe; };   // probe: nullptr in frames; rtx_shadow_probe reads (lit, occluder item, toi bits, face) per ray
+struct ShadowQ { float4* o; float4* d; float4* c; uint32_t* r; uint4* probe; uint4* beyond; };   // beyond: (ray, occluder key bits, occluder item, -) for shadow_beyond_kernel   // probe: nullptr in frames; rtx_shadow_probe reads (lit, occluder item, toi bits, face) per ray
 struct alignas(16) HitRec { float t; uint32_t item; uint32_t prim; uint32_t flags; };   // item = ~0u: miss
 enum : uint32_t { HF_BACK = 1u, HF_INSIDE = 2u, HF_NEGN = 4u };   // HF_NEGN: parry returned -normalize(n) (t < 0 branch)
 enum : uint32_t { RF_ID_OWNER = 1u };
@@ -99,6 +103,7 @@ struct Counters {      // device counters, 64-bit
     // [0] steps (per warp)  [1] lanes with a ray, summed over steps  [2] lanes in the NODE phase  [3] LEAF rounds  [4] lanes in LEAF rounds
     // [5] refills  [6] lanes refilled
     unsigned long long phase[2][8];
+    unsigned long long beyond_rays, beyond_found;   // shadow_beyond_kernel: rays checked / rays sent on to the exact walk
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -658,7 +663,7 @@ struct Lane {
 __device__ __forceinline__ void lane_init(Lane& L, const SceneDev& S, float3 o, float3 d, float tmax) {
     L.w = make_wide_ray(o, d); L.r = L.w; L.tmax = tmax;
     if (S.flat_items) { L.ng = make_uint2(0u, 0u); L.tg = make_uint2(0u, S.flat_items); }      // few items: every item is a leaf entry, no TLAS node
-    else { L.ng = make_uint2(S.tlas_root, 0x80000000u); L.tg = make_uint2(0u, 0u); }
+    else { L.ng = make_uint2(S.fast_root, 0x80000000u); L.tg = make_uint2(0u, 0u); }
     L.sp = 0; L.blas_base = -1;
     L.cur_item = 0; L.cur_key = 0.0f; L.bkey = 0.0f; L.bitem = 0xFFFFFFFFu; L.bprim = 0; L.bface = 0xFFFFFFFFu; L.bflags = 0;
 }
@@ -724,6 +729,94 @@ __device__ __forceinline__ void lane_any_hit(Lane& L, float key, uint32_t item, 
     if (!S.any_alpha_tex && L.tmax >= 3.402823466e+38f) L.sp = 0;
 }
 
+// Merged world-space BLAS ("the group").  glTF scenes arrive as dozens of mesh items that all carry the identity transform
+// (Scene::load_gltf bakes node transforms into the vertices, reference src/scene.rs:853-891); their boxes overlap heavily, so a
+// TLAS over them sends every ray through several instance entries.  The host therefore also builds ONE BVH over all their
+// triangles (object space == world space), each triangle tagged with its item.  What the reference does per ITEM is applied
+// lazily per accepted triangle: the item filter of raytracing.rs:454 and the exact local-space slab test (`intersect_b_box`,
+// which both admits the item and yields the sort key of :466).  cur_item = 0x80000000 | cached item (0x7FFFFFFF: none) marks
+// group mode; cur_key = that item's key, NaN when the item is filtered out or its slab test fails.
+__device__ __forceinline__ void group_item_key(const SceneDev& S, uint32_t ii, float3 o, float3 d, bool for_shadow, uint32_t depth, float& key) {
+    const DItem* it = S.items + ii;
+    const uint32_t flags = it->flags;
+    key = __int_as_float(0x7fc00000);
+    if (!item_passes(flags, for_shadow, depth)) return;
+    const float4 lo = __ldg(&it->lo), hi = __ldg(&it->hi);
+    float k;
+    if (aabb_cast(f3(lo.x, lo.y, lo.z), f3(hi.x, hi.y, hi.z), o, d, item_solid(flags, for_shadow), k)) key = k;
+}
+
+// Shadow rays with a finite light distance whose occluder A is known (shadow_any_kernel): the reference stops at the FIRST item,
+// in (bbox key, index) order, that is hit at all, and calls the ray lit when that hit lies beyond the light (raytracing.rs:466-487,
+// 885-892).  "Occluded" can therefore only be wrong if some item sorted before A is hit beyond the light.  For the grouped items
+// that is one any-hit query on the merged BLAS over (len, inf): true = such an item may exist (the ray goes to the exact walk).
+// Stage 1 is a point query on the item TLAS: an item B that is entered before A (key_B < key_A <= len) and hit beyond the light
+// holds the whole ray segment from key_B to that hit inside its box, in particular the point at the light distance — so only
+// items whose box contains o + d * len (conservatively) can matter, and for most light positions there is none.
+template <bool STATS>
+__device__ __forceinline__ bool group_hit_beyond_light(const SceneDev& S, float3 o, float3 d, float len, float key_a, uint32_t item_a, uint32_t depth, TravStats& st) {
+    const WideRay r = make_wide_ray(o, d);
+    uint2 stack[kStack]; int sp = 0;
+    uint2 ngroup = make_uint2(S.tlas_root, 0x80000000u), tgroup = make_uint2(0u, 0u);
+    bool suspect = false;
+    const float t_lo = len * 0.9999f - 1e-6f, t_hi = len * 1.0001f + 1e-6f;
+    for (;;) {
+        if (ngroup.y > 0x00FFFFFFu) {
+            const uint32_t imask = ngroup.y;
+            const uint32_t cbit = bfind(imask);
+            const uint32_t base = ngroup.x;
+            ngroup.y &= ~(1u << cbit);
+            if (ngroup.y > 0x00FFFFFFu) { if (sp >= kStack) return true; stack[sp++] = ngroup; }
+            const uint32_t slot = (cbit - 24u) ^ (r.octinv4 & 0xffu);
+            const uint32_t rel = __popc(imask & ~(0xFFFFFFFFu << slot));
+            if (STATS) st.nodes++;
+            node_test(S.nodes, base + rel, r, t_lo, t_hi, ngroup, tgroup);
+        } else { tgroup = ngroup; ngroup = make_uint2(0u, 0u); }
+        while (tgroup.y != 0u) {
+            const uint32_t ti = bfind(tgroup.y);
+            tgroup.y &= ~(1u << ti);
+            const uint32_t ii = __ldg(S.tlas_prims + tgroup.x + ti);
+            if (!(S.items[ii].flags & IF_GROUPED)) continue;
+            float kb; group_item_key(S, ii, o, d, true, depth, kb);
+            if (kb == kb && (kb < key_a || (kb == key_a && ii < item_a))) suspect = true;
+        }
+        if (suspect) break;
+        if (ngroup.y <= 0x00FFFFFFu) { if (sp == 0) break; ngroup = stack[--sp]; }
+    }
+    if (!suspect) return false;
+    sp = 0;
+    ngroup = make_uint2(S.group_root, 0x80000000u); tgroup = make_uint2(0u, 0u);
+    uint32_t c_item = 0xFFFFFFFFu; float c_key = 0.0f;
+    for (;;) {
+        if (ngroup.y > 0x00FFFFFFu) {
+            const uint32_t imask = ngroup.y;
+            const uint32_t cbit = bfind(imask);
+            const uint32_t base = ngroup.x;
+            ngroup.y &= ~(1u << cbit);
+            if (ngroup.y > 0x00FFFFFFu) { if (sp >= kStack) return true; stack[sp++] = ngroup; }
+            const uint32_t slot = (cbit - 24u) ^ (r.octinv4 & 0xffu);
+            const uint32_t rel = __popc(imask & ~(0xFFFFFFFFu << slot));
+            if (STATS) st.nodes++;
+            node_test(S.nodes, base + rel, r, len, 3.402823466e+38f, ngroup, tgroup);
+        } else { tgroup = ngroup; ngroup = make_uint2(0u, 0u); }
+        while (tgroup.y != 0u) {
+            const uint32_t ti = bfind(tgroup.y);
+            tgroup.y &= ~(1u << ti);
+            const float4* tp = S.tris + (size_t)(tgroup.x + ti) * 3;
+            const float4 v0 = __ldg(tp), v1 = __ldg(tp + 1), v2 = __ldg(tp + 2);
+            if (STATS) st.tris++;
+            float toi; uint32_t back;
+            if (tri_cast(f3(v0.x, v0.y, v0.z), f3(v1.x, v1.y, v1.z), f3(v2.x, v2.y, v2.z), o, d, toi, back) && toi > len) {
+                const uint32_t ii = __float_as_uint(v1.w);
+                if (ii != c_item) { group_item_key(S, ii, o, d, true, depth, c_key); c_item = ii; }
+                if (c_key == c_key && (c_key < key_a || (c_key == key_a && ii < item_a))) return true;
+            }
+        }
+        if (ngroup.y <= 0x00FFFFFFu) { if (sp == 0) break; ngroup = stack[--sp]; }
+    }
+    return false;
+}
+
 // WHICH: 0 = whatever the entry is; 1 = the caller knows it is a triangle (L.blas_base >= 0); 2 = an item of the TLAS.
 // The kernels run triangles and items in separate rounds: the two paths share no code, so a mixed round would execute
 // both at a fraction of the lanes each.
@@ -739,12 +832,34 @@ __device__ __forceinline__ void lane_leaf(Lane& L, uint2* stack, const SceneDev&
         if (STATS) st.tris++;
         float toi; uint32_t back;
         if (tri_cast(f3(v0.x, v0.y, v0.z), f3(v1.x, v1.y, v1.z), f3(v2.x, v2.y, v2.z), L.r.o, L.r.d, toi, back)) {
-            if (MODE == UT_CLOSEST) lane_accept(L, toi, L.cur_key, L.cur_item, prim, __float_as_uint(v0.w), back);
+            if (L.cur_item & 0x80000000u) {                               // triangle of the merged BLAS: item work only for a hit that would be taken
+                const bool cand = (MODE == UT_CLOSEST) ? (toi < L.tmax || (toi == L.tmax && L.bitem != 0xFFFFFFFFu)) : (toi <= L.tmax);
+                if (cand) {
+                    const uint32_t ii = __float_as_uint(v1.w);
+                    if ((L.cur_item & 0x7FFFFFFFu) != ii) { group_item_key(S, ii, L.w.o, L.w.d, for_shadow, depth, L.cur_key); L.cur_item = 0x80000000u | ii; }
+                    if (L.cur_key == L.cur_key) {
+                        if (MODE == UT_CLOSEST) lane_accept(L, toi, L.cur_key, ii, prim, __float_as_uint(v0.w), back);
+                        else lane_any_hit(L, L.cur_key, ii, S);
+                    }
+                }
+            } else if (MODE == UT_CLOSEST) lane_accept(L, toi, L.cur_key, L.cur_item, prim, __float_as_uint(v0.w), back);
             else if (toi <= L.tmax) lane_any_hit(L, L.cur_key, L.cur_item, S);
         }
         return;
     }
-    const uint32_t ii = __ldg(S.tlas_prims + prim);                       // item of the TLAS
+    const uint32_t ii = __ldg(S.fast_prims + prim);                       // entry of the fast TLAS
+    if (ii == kGroupPrim) {                                               // the merged BLAS: world space, no item work at entry
+        if (MODE == UT_ANY && L.bflags != 0u) return;                     // occluder known: grouped items are not enumerated (shadow_beyond_kernel settles their order)
+#ifndef RTX_NO_GUARD
+        if (L.sp + 2 > kLaneStack) { lane_abort(L, S); return; }
+#endif
+        if (L.ng.y > 0x00FFFFFFu) stack[L.sp++] = L.ng;
+        if (L.tg.y != 0u) stack[L.sp++] = L.tg;
+        L.blas_base = L.sp; L.cur_item = 0xFFFFFFFFu; L.cur_key = 0.0f;
+        L.r = L.w;
+        L.ng = make_uint2(S.group_root, 0x80000000u); L.tg = make_uint2(0u, 0u);
+        return;
+    }
     const DItem* it = S.items + ii;
     const uint32_t flags = it->flags;
     if (!item_passes(flags, for_shadow, depth)) return;

@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(kTraceBlock, RTX_MIN_BLOCKS) shadow_any_kernel
     for (;;) {
         // write-back of the rays that ended since the last refill, all at once (the lanes that are about to be refilled)
         {
-            bool to_slow = false;
+            bool to_slow = false, to_beyond = false;
             if (fin) {
                 fin = false;
                 const bool occluded = L.bitem != 0xFFFFFFFFu;
@@ -227,13 +227,18 @@ __global__ void __launch_bounds__(kTraceBlock, RTX_MIN_BLOCKS) shadow_any_kernel
                 const bool earlier_other = L.bface != 0xFFFFFFFFu && (okey < L.bkey || (okey == L.bkey && L.bface < L.bitem));
                 // final unless the reference's first-hit order could change the answer: an alpha-textured material exists, or (finite
                 // light distance and) another candidate sorts before the occluder, or the occluder's own key lies beyond the light
-                // (then the clipped item walk may not have seen every earlier candidate)
-                if (!occluded || (!S.any_alpha_tex && (L.tmax >= 3.402823466e+38f || (!earlier_other && !(L.bkey > L.tmax))))) {
+                // (then the clipped item walk may not have seen every earlier candidate).  With a merged BLAS the grouped items are
+                // not enumerated: whether one of them sorts before the occluder AND is hit beyond the light is asked afterwards, only
+                // for occluded rays with a finite light distance (shadow_beyond_kernel).
+                if (!occluded || (!S.any_alpha_tex && L.tmax >= 3.402823466e+38f)) to_slow = false;
+                else if (S.any_alpha_tex || earlier_other || L.bkey > L.tmax) to_slow = true;
+                else if (S.group_root != 0xFFFFFFFFu) to_beyond = true;
+                if (!to_slow && !to_beyond) {
                     const float4 rc = q.c[my];
                     const float k = occluded ? 1.0f - rc.w : 1.0f;               // raytracing.rs:898,912
                     atomicAdd(&F.accum_c[__float_as_uint(q.d[my].w)], make_float4(rc.x * k, rc.y * k, rc.z * k, 0.0f));
                     if (q.probe) q.probe[my] = make_uint4(occluded ? 0u : 1u, L.bitem, 0xFFFFFFFFu, 0u);   // rtx_shadow_probe only
-                } else to_slow = true;
+                }
             }
             const uint32_t sm = __ballot_sync(kFull, to_slow);
             if (sm != 0u) {
@@ -242,6 +247,14 @@ __global__ void __launch_bounds__(kTraceBlock, RTX_MIN_BLOCKS) shadow_any_kernel
                 if (lane == leader) base = atomicAdd(slow_count, __popc(sm));
                 base = __shfl_sync(kFull, base, leader);
                 if (to_slow) slow[base + __popc(sm & ((1u << lane) - 1u))] = my;
+            }
+            const uint32_t bm = __ballot_sync(kFull, to_beyond);
+            if (bm != 0u) {
+                const uint32_t leader = __ffs(bm) - 1u;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(slow_count + 1, __popc(bm));      // ctr[5]: beyond-light queue
+                base = __shfl_sync(kFull, base, leader);
+                if (to_beyond) q.beyond[base + __popc(bm & ((1u << lane) - 1u))] = make_uint4(my, __float_as_uint(L.bkey), L.bitem, 0u);
             }
         }
         const uint32_t idle = __ballot_sync(kFull, !has);
@@ -310,6 +323,33 @@ __global__ void __launch_bounds__(kTraceBlock, RTX_MIN_BLOCKS) shadow_any_kernel
         atomicAdd(&ctr->node_visits[1], (unsigned long long)st.nodes); atomicAdd(&ctr->tri_tests[1], (unsigned long long)st.tris);
         atomicAdd(&ctr->item_tests, (unsigned long long)n_items); atomicAdd(&ctr->sphere_tests, (unsigned long long)n_sph);
         for (int k = 0; k < 7; k++) atomicAdd(&ctr->phase[1][k], (unsigned long long)ph[k]);
+    }
+}
+
+// K3a': occluded rays with a finite light distance, scenes with a merged BLAS (see group_hit_beyond_light).  Not found (the usual
+// case: nothing the ray meets behind the light sorts before the occluder) -> the ray is occluded, final; found -> exact walk.
+template <bool STATS>
+__global__ void __launch_bounds__(kTraceBlock) shadow_beyond_kernel(SceneDev S, FrameDev F, ShadowQ q, const uint32_t* __restrict__ n_ptr, uint32_t n_cap, uint32_t depth,
+                                                                    uint32_t* __restrict__ slow, uint32_t* slow_count, Counters* ctr) {
+    TravStats st{0, 0}; uint32_t found = 0, seen = 0;
+    const uint32_t n = min(*n_ptr, n_cap);
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const uint4 e = q.beyond[j];
+        const uint32_t i = e.x;
+        const float4 ro = q.o[i], rd = q.d[i];
+        seen++;
+        if (group_hit_beyond_light<STATS>(S, f3(ro.x, ro.y, ro.z), f3(rd.x, rd.y, rd.z), ro.w, __uint_as_float(e.y), e.z, depth, st)) {
+            slow[atomicAdd(slow_count, 1u)] = i; found++;
+        } else {
+            const float4 rc = q.c[i];
+            const float k = 1.0f - rc.w;
+            atomicAdd(&F.accum_c[__float_as_uint(rd.w)], make_float4(rc.x * k, rc.y * k, rc.z * k, 0.0f));
+            if (q.probe) q.probe[i] = make_uint4(0u, e.z, 0xFFFFFFFFu, 0u);
+        }
+    }
+    if (STATS) {
+        atomicAdd(&ctr->node_visits[1], (unsigned long long)st.nodes); atomicAdd(&ctr->tri_tests[1], (unsigned long long)st.tris);
+        atomicAdd(&ctr->beyond_rays, (unsigned long long)seen); atomicAdd(&ctr->beyond_found, (unsigned long long)found);
     }
 }
 

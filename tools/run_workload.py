@@ -16,6 +16,8 @@ frames = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 want_stats = len(sys.argv) > 3 and sys.argv[3] == "stats"
 fs, cam, cfg, desc = bench.build_workload(name)
 g = RendererManager(cam.width, cam.height, fs)
+info = g.bvh_info()
+desc.update({"scene_build_ms": info.build_ms, "grouped_items": info.grouped_items, "grouped_triangles": info.grouped_triangles, "bvh_nodes": info.n_nodes})
 print(json.dumps(desc))
 if want_stats:
     c = abi.RtxConfig(); C.memmove(C.byref(c), C.byref(cfg), C.sizeof(cfg)); c.debug_flags = 1
@@ -27,6 +29,6 @@ if want_stats:
 g.start(cam, cfg)
 for _ in range(frames):
     s = g.start(cam, cfg).stats
-    print("frame: %.2f ms device (closest %.2f, shadow %.2f, shade+rest %.2f) | %d closest + %d shadow rays (%d via the exact walk) | %.1f Mrays/s | waves %d, syncs %d, launches %d" % (
-        s.device_ms, s.closest_ms, s.shadow_ms, s.shade_ms, s.rays_closest, s.rays_shadow, s.rays_shadow_exact, (s.rays_closest + s.rays_shadow) / s.device_ms / 1e3,
+    print("frame: %.2f ms device (closest %.2f, shadow %.2f, shade+rest %.2f) | %d closest + %d shadow rays (%d beyond-light checks, %d via the exact walk) | %.1f Mrays/s | waves %d, syncs %d, launches %d" % (
+        s.device_ms, s.closest_ms, s.shadow_ms, s.shade_ms, s.rays_closest, s.rays_shadow, s.rays_shadow_beyond, s.rays_shadow_exact, (s.rays_closest + s.rays_shadow) / s.device_ms / 1e3,
         s.waves, s.host_syncs, s.kernel_launches))
