@@ -185,7 +185,7 @@ __device__ __forceinline__ float mc_uniform(uint32_t seed, uint32_t pixel, uint3
 // primitive tests (restating parry3d 0.13; see oracle/rt_oracle.cpp for the citations)
 // ------------------------------------------------------------------------------------------------
 // Aabb::cast_local_ray(ray, f32::MAX, solid) — reference call sites src/shape/sphere.rs:51, mesh.rs:58
-__device__ __forceinline__ bool aabb_cast(float3 lo, float3 hi, float3 o, float3 d, bool solid, float& key) {
+__device__ __forceinline__ bool aabb_cast(float3 lo, float3 hi, float3 o, float3 d, bool solid, float& key, float* t_exit = nullptr) {
     float tmin = 0.0f, tmax = 3.402823466e+38f;
     const float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z}, mn[3] = {lo.x, lo.y, lo.z}, mx[3] = {hi.x, hi.y, hi.z};
 #pragma unroll
@@ -202,6 +202,7 @@ __device__ __forceinline__ bool aabb_cast(float3 lo, float3 hi, float3 o, float3
         }
     }
     key = (tmin == 0.0f && !solid) ? tmax : tmin;
+    if (t_exit) *t_exit = tmax;
     return true;
 }
 
@@ -884,20 +885,25 @@ __device__ __forceinline__ void lane_leaf(Lane& L, uint2* stack, const SceneDev&
     }
     const float4 lo = __ldg(&it->lo), hi = __ldg(&it->hi);
     const bool solid = item_solid(flags, for_shadow);
-    float key;
+    float key, t_exit;
     if (STATS) n_items++;
-    if (!aabb_cast(f3(lo.x, lo.y, lo.z), f3(hi.x, hi.y, hi.z), lo3, ld3, solid, key)) return;
-    if (MODE == UT_ANY && L.bflags != 0u) { lane_note_other(L, key, ii); return; }    // occluder known: only enumerate
+    if (!aabb_cast(f3(lo.x, lo.y, lo.z), f3(hi.x, hi.y, hi.z), lo3, ld3, solid, key, &t_exit)) return;
+    // UT_ANY: which OTHER candidates can turn "occluded" into the reference's "lit"?  Only an item that sorts before the occluder and
+    // whose first hit lies BEYOND the light (raytracing.rs:466-487, 885-892).  Its hits lie inside its box, so a box the ray leaves
+    // before the light cannot hold one: such a candidate either has a hit in front of the light (same verdict) or none (not a
+    // candidate at all) and need not be noted.  The margin covers the few ulps between a triangle's toi and its box's slab distance.
+    const bool reaches_light = MODE == UT_ANY && fmaf(t_exit, 1.0001f, 1e-6f) >= L.tmax;
+    if (MODE == UT_ANY && L.bflags != 0u) { if (reaches_light) lane_note_other(L, key, ii); return; }    // occluder known: only enumerate
     if (!(flags & IF_MESH)) {
         float t; bool inside;
         if (STATS) n_sph++;
         const bool h = ball_cast(lo.w, lo3, ld3, solid, t, inside);
         if (MODE == UT_CLOSEST) { if (h) lane_accept(L, t, key, ii, 0u, 0u, inside ? HF_INSIDE : 0u); }
         else if (h && t <= L.tmax) lane_any_hit(L, key, ii, S);
-        else lane_note_other(L, key, ii);
+        else if (h) lane_note_other(L, key, ii);                          // hit only beyond the light: the one kind of candidate that matters
         return;
     }
-    if (MODE == UT_ANY) lane_note_other(L, key, ii);                      // harmless if it becomes the occluder: (key, item) is then not < itself
+    if (MODE == UT_ANY && reaches_light) lane_note_other(L, key, ii);     // harmless if it becomes the occluder: (key, item) is then not < itself
     // enter the instance: park what is left of the TLAS groups under the BLAS part of the stack
 #ifndef RTX_NO_GUARD
     if (L.sp + 2 > kLaneStack) { lane_abort(L, S); return; }

@@ -111,6 +111,10 @@ constexpr uint32_t kFull = 0xffffffffu;
 #define RTX_ITEM_BATCH 4
 #endif
 constexpr int kItemBatch = RTX_ITEM_BATCH;
+#ifndef RTX_LEAF_BATCH_ANY
+#define RTX_LEAF_BATCH_ANY RTX_LEAF_BATCH   // any-hit rays end at their first hit: postponing triangle tests costs node visits the hit would have saved
+#endif
+constexpr int kLeafBatchAny = RTX_LEAF_BATCH_ANY;
 #ifndef RTX_TRI_REPS
 #define RTX_TRI_REPS 2                      // triangles handled per lane in one triangle round
 #endif
@@ -290,7 +294,7 @@ __global__ void __launch_bounds__(kTraceBlock, RTX_MIN_BLOCKS) shadow_any_kernel
                 const bool want_tri = has && L.tg.y != 0u && L.blas_base >= 0, want_item = has && L.tg.y != 0u && L.blas_base < 0;
                 const uint32_t mt = __ballot_sync(kFull, want_tri), mi = __ballot_sync(kFull, want_item);
                 const bool no_nodes = !__any_sync(kFull, has && L.ng.y > 0x00FFFFFFu);
-                if (mt != 0u && (__popc(mt) >= kLeafBatch || no_nodes)) {
+                if (mt != 0u && (__popc(mt) >= kLeafBatchAny || no_nodes)) {
                     if (STATS) { ph[3] += (lane == 0); ph[4] += want_tri; }
                     if (want_tri) {
                         lane_leaf<UT_ANY, STATS, 1>(L, stack, S, true, depth, st, n_items, n_sph);
