@@ -329,6 +329,11 @@ const char* rtx_last_error(void);
 int rtx_abi_version(void);
 int rtx_device_count(void);
 
+/* The host-side wide-BVH builder on n boxes (6 floats each: lo.xyz, hi.xyz), no device involved: depth and node count of
+ * the tree and its leaf order.  depth_limit > 0 = the limit rtx_scene_create applies (a deeper SAH tree is rebuilt balanced). */
+int rtx_bvh_build_probe(const float* boxes, uint32_t n, int depth_limit, uint32_t* max_depth, uint32_t* n_nodes,
+                        uint32_t* prim_order);
+
 /* Read bandwidth of a `bytes`-sized buffer swept `iters` times with 128-bit loads (ld.global.cg): with bytes well below
  * the 126 MB L2 this is the L2 figure SURVEY.md §8(d) asks to quote next to the HBM roofline for L2-resident scenes. */
 int rtx_bandwidth_probe(int device, uint64_t bytes, uint32_t iters, float* gbytes_per_s);

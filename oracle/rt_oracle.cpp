@@ -159,6 +159,11 @@ void build_sample_table(uint32_t samples, uint32_t* cell_size, std::vector<uint1
 // Must stay identical to rustray_b200/csrc (both are checked against each other in tests).
 // ------------------------------------------------------------------------------------------
 inline uint32_t mix32(uint32_t h) { h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16; return h; }
+// Id of a child ray in the reflection / refraction tree (the Monte-Carlo stream key): 2 * path + which is unique down to depth
+// 31; deeper (max_recursion > 30) the 32-bit id would wrap and streams collide, so it is hashed with the depth instead.
+inline uint32_t child_path(uint32_t path, uint32_t which, uint32_t depth) {
+    return depth < 31u ? path * 2u + which : mix32(path * 0x9E3779B1u + which + (depth << 8));
+}
 inline float mc_uniform(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t path, uint32_t slot) {
     uint32_t h = mix32(seed ^ 0x9E3779B9u);
     h = mix32(h ^ (pixel * 0x85EBCA6Bu + 0x165667B1u));
@@ -721,13 +726,13 @@ Radiance shade(const Scene& sc, const RtxConfig& cfg, Ray ray, uint32_t depth, c
     color = color * (1.0f - reflectivity);
     if (reflectivity > 0.0f && depth <= cfg.max_recursion) {                                 // :938-945
         Ray rr = create_reflection(surface_normal, r.d, hit_point);
-        V3 rc = shade(sc, cfg, rr, depth + 1, mc, path * 2, cnt).color;
+        V3 rc = shade(sc, cfg, rr, depth + 1, mc, child_path(path, 0, depth), cnt).color;
         color = color + (rc * reflectivity);
     }
     if (alpha < 1.0f && depth <= cfg.max_recursion) {                                        // :948-975
         Ray tr;
         if (create_transmission(surface_normal, r.d, hit_point, refraction_index, &tr)) {
-            Radiance t = shade(sc, cfg, tr, depth + 1, mc, path * 2 + 1, cnt);
+            Radiance t = shade(sc, cfg, tr, depth + 1, mc, child_path(path, 1, depth), cnt);
             if (kr < 1.0f) color = (color * alpha) + (t.color * (1.0f - kr) * (1.0f - alpha));
             else color = (color * alpha) + (t.color * (1.0f - alpha));
             if (approx_equal(alpha, 0.0f)) out.id = t.id;

@@ -298,6 +298,7 @@ def bind(lib: C.CDLL, prefix: str = "rtx_") -> None:
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
         "shard_unpack_all": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+        "bvh_build_probe": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, P(C.c_uint32), P(C.c_uint32), C.c_void_p]),
         "bandwidth_probe": (C.c_int, [C.c_int, C.c_uint64, C.c_uint32, P(C.c_float)]),
         "render_frame_async": (C.c_int, [C.c_void_p, P(RtxCamera), P(RtxConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
         "render_poll": (C.c_int, [C.c_void_p, P(C.c_uint64), P(C.c_int), P(C.c_int), P(C.c_int), P(RtxStats)]),
@@ -335,7 +336,7 @@ ABI_SYMBOLS = ["rtx_scene_create", "rtx_scene_update_items", "rtx_scene_set_ligh
                "rtx_scene_destroy", "rtx_last_error", "rtx_abi_version", "rtx_device_count",
                "rtx_post_process_device", "rtx_shadow_probe", "rtx_scene_create_multi", "rtx_scene_device_count",
                "rtx_gbuffer_create", "rtx_gbuffer_export", "rtx_gbuffer_open", "rtx_gbuffer_pointers", "rtx_gbuffer_download",
-               "rtx_gbuffer_destroy", "rtx_shard_unpack_all", "rtx_bandwidth_probe"]
+               "rtx_gbuffer_destroy", "rtx_shard_unpack_all", "rtx_bandwidth_probe", "rtx_bvh_build_probe"]
 
 
 def fixture_path(name: str) -> str:

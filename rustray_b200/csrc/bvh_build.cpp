@@ -21,6 +21,7 @@ struct Node2 {
     Aabb3 box;
     int32_t left = -1, right = -1;   // children (internal) ...
     uint32_t first = 0, count = 0;   // ... or primitive range (leaf, count > 0)
+    uint32_t total = 0;              // primitives below this node (balanced collapse)
 };
 
 inline void grow(Aabb3& a, const Aabb3& b) {
@@ -41,6 +42,7 @@ struct Builder2 {
     std::vector<uint32_t> idx;
     std::vector<float> cen;     // 3 per primitive
     std::vector<Node2> nodes;
+    bool balanced = false;      // object-median splits: depth <= ceil(log2 n), used when the SAH tree is too deep for the traversal stack
 
     void build(uint32_t n) {
         idx.resize(n); cen.resize(3 * (size_t)n);
@@ -60,11 +62,24 @@ struct Builder2 {
                 grow(box, boxes[p]);
                 for (int k = 0; k < 3; k++) { cb.lo[k] = std::min(cb.lo[k], cen[3 * (size_t)p + k]); cb.hi[k] = std::max(cb.hi[k], cen[3 * (size_t)p + k]); }
             }
-            nodes[j.node].box = box;
+            nodes[j.node].box = box; nodes[j.node].total = j.count;
             if (j.count == 1) { nodes[j.node].first = j.first; nodes[j.node].count = 1; continue; }
 
             // binned SAH over the three axes
             float best_cost = std::numeric_limits<float>::infinity(); int best_axis = -1, best_split = -1;
+            if (balanced) {
+                if (j.count <= kMaxLeaf) { nodes[j.node].first = j.first; nodes[j.node].count = j.count; continue; }
+                int ax = 0; for (int k = 1; k < 3; k++) if (cb.hi[k] - cb.lo[k] > cb.hi[ax] - cb.lo[ax]) ax = k;
+                const uint32_t mid = j.first + j.count / 2;
+                std::nth_element(idx.begin() + j.first, idx.begin() + mid, idx.begin() + j.first + j.count,
+                                 [&](uint32_t a, uint32_t b) { return cen[3 * (size_t)a + ax] < cen[3 * (size_t)b + ax]; });
+                int32_t l = (int32_t)nodes.size();
+                nodes.emplace_back(); nodes.emplace_back();
+                nodes[j.node].left = l; nodes[j.node].right = l + 1;
+                stack.push_back({l, j.first, mid - j.first});
+                stack.push_back({l + 1, mid, j.first + j.count - mid});
+                continue;
+            }
             for (int ax = 0; ax < 3; ax++) {
                 float ext = cb.hi[ax] - cb.lo[ax];
                 if (!(ext > 0.f)) continue;
@@ -124,9 +139,9 @@ struct WideBuilder {
         int32_t ch[8]; int nch = 0;
         if (N[n2_root].count > 0) ch[nch++] = n2_root;     // degenerate: the whole tree is one leaf
         else { ch[nch++] = N[n2_root].left; ch[nch++] = N[n2_root].right; }
-        while (nch < 8) {                                   // greedy: open the largest internal child
+        while (nch < 8) {                                   // greedy: open the largest internal child (by area; by size in a balanced tree)
             int best = -1; float ba = -1.f;
-            for (int i = 0; i < nch; i++) if (N[ch[i]].count == 0) { float a = half_area(N[ch[i]].box); if (a > ba) { ba = a; best = i; } }
+            for (int i = 0; i < nch; i++) if (N[ch[i]].count == 0) { float a = b2.balanced ? (float)N[ch[i]].total : half_area(N[ch[i]].box); if (a > ba) { ba = a; best = i; } }
             if (best < 0) break;
             int32_t c = ch[best];
             ch[best] = N[c].left; ch[nch++] = N[c].right;
@@ -229,16 +244,23 @@ struct WideBuilder {
 
 }  // namespace
 
-void build_wide_bvh(const Aabb3* boxes, uint32_t n, WideBvh& out) {
-    out.nodes.clear(); out.prim_order.clear(); out.max_depth = 0;
-    if (n == 0) return;
-    Builder2 b2; b2.boxes = boxes;
-    b2.build(n);
-    out.nodes.reserve(n / 2 + 8);
-    out.prim_order.reserve(n);
-    out.nodes.emplace_back();
-    WideBuilder wb{b2, out};
-    wb.emit(0, 0, 1);
+void build_wide_bvh(const Aabb3* boxes, uint32_t n, WideBvh& out, int depth_limit) {
+    for (int pass = 0; pass < 2; pass++) {
+        out.nodes.clear(); out.prim_order.clear(); out.max_depth = 0;
+        if (n == 0) return;
+        Builder2 b2; b2.boxes = boxes;
+        b2.balanced = pass == 1;
+        b2.build(n);
+        out.nodes.reserve(n / 2 + 8);
+        out.prim_order.reserve(n);
+        out.nodes.emplace_back();
+        WideBuilder wb{b2, out};
+        wb.emit(0, 0, 1);
+        // the greedy largest-area collapse does not bound the depth along small-area paths of an unbalanced SAH tree: a tree
+        // that would not fit the traversal stack is rebuilt with object-median splits and a size-balanced collapse
+        // (depth ~ log8 n) instead of being refused
+        if (depth_limit <= 0 || out.max_depth <= depth_limit) return;
+    }
 }
 
 }  // namespace rtx

@@ -32,7 +32,8 @@ struct WideBvh {
     int max_depth = 0;
 };
 
-// Build over `n` primitive boxes.  Leaves hold at most 3 primitives.
-void build_wide_bvh(const Aabb3* boxes, uint32_t n, WideBvh& out);
+// Build over `n` primitive boxes.  Leaves hold at most 3 primitives.  depth_limit > 0: a tree deeper than that is rebuilt
+// with object-median splits and a size-balanced collapse (depth ~ log8 n).
+void build_wide_bvh(const Aabb3* boxes, uint32_t n, WideBvh& out, int depth_limit = 0);
 
 }  // namespace rtx

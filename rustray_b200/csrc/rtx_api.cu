@@ -59,6 +59,8 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
     } while (0)
 
 constexpr uint32_t kCtrPool = 1u << 17;   // counters (8 per wave) zeroed in one memset
+// deepest BLAS the traversal stacks hold: kStack - 3 levels for the one-thread walks, 2 * depth + 2 * 6 (TLAS) + 4 <= kLaneStack for the lanes
+constexpr int kBlasDepthLimit = (kStack - 3) < (kLaneStack - 16) / 2 ? (kStack - 3) : (kLaneStack - 16) / 2;
 
 inline bool approx_equal_h(float a, float b) { return std::trunc(a * 1000000.0f) == std::trunc(b * 1000000.0f); }
 
@@ -209,7 +211,7 @@ int build_tlas(RtxScene& sc, std::vector<float4>& tlas_nodes, std::vector<uint32
         sc.h_items[i].wlo = make_float4(boxes[i].lo[0], boxes[i].lo[1], boxes[i].lo[2], 0.f);
         sc.h_items[i].whi = make_float4(boxes[i].hi[0], boxes[i].hi[1], boxes[i].hi[2], 0.f);
     }
-    WideBvh bvh; build_wide_bvh(boxes.data(), (uint32_t)boxes.size(), bvh);
+    WideBvh bvh; build_wide_bvh(boxes.data(), (uint32_t)boxes.size(), bvh, 6);
     if (bvh.max_depth > 6) return fail(RTX_E_INVALID, "TLAS too deep for the traversal stack");
     tlas_nodes.clear();
     append_nodes(tlas_nodes, bvh, sc.n_blas_nodes, 0);
@@ -233,7 +235,7 @@ int build_tlas_fast(RtxScene& sc, std::vector<float4>& nodes, std::vector<uint32
         } else { boxes.push_back(b); ids.push_back((uint32_t)i); }
     }
     if (have_group) { boxes.push_back(gb); ids.push_back(kGroupPrim); }
-    WideBvh bvh; build_wide_bvh(boxes.data(), (uint32_t)boxes.size(), bvh);
+    WideBvh bvh; build_wide_bvh(boxes.data(), (uint32_t)boxes.size(), bvh, 6);
     if (bvh.max_depth > 6) return fail(RTX_E_INVALID, "TLAS too deep for the traversal stack");
     nodes.clear();
     append_nodes(nodes, bvh, sc.n_blas_nodes + sc.tlas_cap, 0);
@@ -486,7 +488,7 @@ int rtx_scene_create(const RtxSceneDesc* d, int device, RtxScene** out) {
                     }
                     for (int k = 0; k < 3; k++) { o.lo[k] = std::min(o.lo[k], b.lo[k]); o.hi[k] = std::max(o.hi[k], b.hi[k]); }   // TriMesh::aabb
                 }
-                build_wide_bvh(boxes.data(), m.n_faces, bvhs[mi]);
+                build_wide_bvh(boxes.data(), m.n_faces, bvhs[mi], kBlasDepthLimit);
             }
         };
         const uint32_t nt = std::min<uint32_t>(d->n_meshes, std::max(1u, std::thread::hardware_concurrency()));
@@ -558,7 +560,7 @@ int rtx_scene_create(const RtxSceneDesc* d, int device, RtxScene** out) {
                     p_item[k] = i; p_face[k] = f;
                 }
             }
-            WideBvh bvh; build_wide_bvh(boxes.data(), (uint32_t)gt, bvh);
+            WideBvh bvh; build_wide_bvh(boxes.data(), (uint32_t)gt, bvh, kBlasDepthLimit);
             if (!(bvh.max_depth >= kStack - 2 || 2 * bvh.max_depth + 2 * 6 + 4 > kLaneStack)) {       // too deep: keep the per-item structure only
                 const uint32_t node_off = (uint32_t)(h_nodes.size() / 5), tri_off = (uint32_t)(h_tris.size() / 3);
                 append_nodes(h_nodes, bvh, node_off, tri_off);
@@ -1511,6 +1513,18 @@ int rtx_gbuffer_destroy(RtxGBuffer* g) {
     cudaSetDevice(g->device);
     if (g->owner) cudaFree(g->base); else cudaIpcCloseMemHandle(g->base);
     delete g;
+    return RTX_OK;
+}
+
+// ---- host BVH builder, exposed for the CPU test suite (no device involved) ---------------------------------------
+int rtx_bvh_build_probe(const float* boxes /* n x (lo.xyz, hi.xyz) */, uint32_t n, int depth_limit, uint32_t* max_depth, uint32_t* n_nodes,
+                        uint32_t* prim_order /* n entries or NULL */) {
+    if (!boxes || !n) return fail(RTX_E_INVALID, "bad argument");
+    static_assert(sizeof(Aabb3) == 24, "Aabb3 layout");
+    WideBvh bvh; build_wide_bvh(reinterpret_cast<const Aabb3*>(boxes), n, bvh, depth_limit);
+    if (max_depth) *max_depth = (uint32_t)bvh.max_depth;
+    if (n_nodes) *n_nodes = (uint32_t)bvh.nodes.size();
+    if (prim_order) memcpy(prim_order, bvh.prim_order.data(), (size_t)n * 4);
     return RTX_OK;
 }
 

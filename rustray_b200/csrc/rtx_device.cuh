@@ -177,6 +177,10 @@ __device__ __forceinline__ float mc_draw(uint32_t base, uint32_t path, uint32_t 
     const uint32_t h = mix32(base ^ (path * 0x9E3779B1u + slot * 0x632BE5ABu + 0x7F4A7C15u));
     return __fmul_rn((float)(h >> 8), 1.0f / 16777216.0f);
 }
+// id of a child ray in the reflection / refraction tree — identical to oracle/rt_oracle.cpp child_path
+__device__ __forceinline__ uint32_t child_path(uint32_t path, uint32_t which, uint32_t depth) {
+    return depth < 31u ? path * 2u + which : mix32(path * 0x9E3779B1u + which + (depth << 8));
+}
 __device__ __forceinline__ float mc_uniform(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t path, uint32_t slot) {
     return mc_draw(mc_base(seed, pixel, sample), path, slot);
 }

@@ -615,7 +615,7 @@ __global__ void __launch_bounds__(kShadeBlock, RTX_SHADE_MIN_BLOCKS) shade_kerne
                     const float3 nd = xnormalize_s(refl_d);                         // :722-723 of the recursive call
                     out.child.o[slot] = make_float4(refl_o.x, refl_o.y, refl_o.z, w_refl);
                     out.child.d[slot] = make_float4(nd.x, nd.y, nd.z, __uint_as_float(pixel));
-                    out.child.m[slot] = make_uint2(sample | ((depth + 1) << 16), path * 2u);
+                    out.child.m[slot] = make_uint2(sample | ((depth + 1) << 16), child_path(path, 0u, depth));
                 } else *out.overflow = 1u;
             }
         }
@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(kShadeBlock, RTX_SHADE_MIN_BLOCKS) shade_kerne
                     const float3 nd = xnormalize_s(trans_d);
                     out.child.o[slot] = make_float4(trans_o.x, trans_o.y, trans_o.z, w_trans);
                     out.child.d[slot] = make_float4(nd.x, nd.y, nd.z, __uint_as_float(pixel));
-                    out.child.m[slot] = make_uint2(sample | ((depth + 1) << 16) | (trans_flags << 24), path * 2u + 1u);
+                    out.child.m[slot] = make_uint2(sample | ((depth + 1) << 16) | (trans_flags << 24), child_path(path, 1u, depth));
                 } else *out.overflow = 1u;
             }
         }

@@ -117,3 +117,31 @@ def test_traversal_kernel_votes_are_protected_in_the_built_sass():
     library that is actually shipped."""
     import __graft_entry__ as g
     g.check_vote_convergence(renderer.lib_path())
+
+
+def test_bvh_depth_limit_falls_back_to_a_balanced_tree():
+    """an unbalanced SAH tree must not make rtx_scene_create refuse a scene the reference accepts.  Boxes that
+    shrink geometrically towards a corner make the binned SAH peel off one primitive per level; with the limit the tree is
+    rebuilt with object-median splits and stays within it, and every primitive is still in exactly one leaf."""
+    lib = renderer.load_library()
+    n = 400
+    k = np.arange(n, dtype=np.float64)
+    size = 1000.0 * 0.9 ** k
+    boxes = np.zeros((n, 6), dtype=np.float32)
+    boxes[:, 3:] = size[:, None]                                    # [0, s]^3, nested
+    depth, nodes = C.c_uint32(), C.c_uint32()
+    order = np.zeros(n, dtype=np.uint32)
+    assert lib.rtx_bvh_build_probe(boxes.ctypes.data, n, 0, C.byref(depth), C.byref(nodes), order.ctypes.data) == 0
+    unlimited = depth.value
+    assert sorted(order.tolist()) == list(range(n))
+    assert lib.rtx_bvh_build_probe(boxes.ctypes.data, n, 6, C.byref(depth), C.byref(nodes), order.ctypes.data) == 0
+    assert depth.value <= 6 and sorted(order.tolist()) == list(range(n))
+    assert unlimited > 6, "the test scene no longer provokes a deep SAH tree (%d)" % unlimited
+    # a well-behaved set is left alone by the limit
+    rng = np.random.default_rng(0)
+    c = rng.uniform(-10, 10, (5000, 3)).astype(np.float32)
+    b2 = np.concatenate([c - 0.1, c + 0.1], axis=1).astype(np.float32)
+    d0, d1 = C.c_uint32(), C.c_uint32()
+    lib.rtx_bvh_build_probe(b2.ctypes.data, 5000, 0, C.byref(d0), C.byref(nodes), None)
+    lib.rtx_bvh_build_probe(b2.ctypes.data, 5000, 16, C.byref(d1), C.byref(nodes), None)
+    assert d0.value == d1.value <= 8

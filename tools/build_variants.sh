@@ -10,3 +10,8 @@ for v in $1; do
 done
 wait
 ls variants
+# the same SASS check the product build gets: every warp vote of the traversal kernels must carry its BRA.DIV / WARPSYNC guard
+cd .. && python -c "
+import glob, __graft_entry__ as g
+for f in sorted(glob.glob('rustray_b200/variants/*.so')):
+    g.check_vote_convergence(f); print('votes guarded:', f)"
