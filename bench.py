@@ -372,6 +372,17 @@ def measure_workload(H, name, steps, warmup, with_cpu, peak, peak_src, l2_gbs, t
                 rh = cpu_oracle_sample(fs, cam, cfg, faithful=False, cell_step=r["cell_step"])
                 out["cpu_baseline"]["hoisted"] = {"value": rh["value"], "unit": UNIT, "sample": rh["sample"]}
             out["speedup_e2e_vs_cpu"] = e2e_val / r["value"]
+        if name == "c5" and H.world == 1:
+            # the same scene with its BVHs built by kernels (RTX_SCENE_DEVICE_BVH): build time, and what the Morton tree costs per frame
+            t0 = time.perf_counter()
+            rd = RendererManager(w, h, fs, device=H.local, device_bvh=True)
+            wall = (time.perf_counter() - t0) * 1e3
+            di = rd.bvh_info()
+            st_d = abi.RtxStats()
+            rd._check(rd._lib.rtx_render_frame_device(rd._h, C.byref(cam), C.byref(cfg), None, ptrs[0], ptrs[1], ptrs[2], ptrs[3], C.c_void_p(stream), C.byref(st_d)))
+            out["device_bvh"] = {"scene_build_ms": di.build_ms, "builder_kernels_ms": di.device_build_ms, "create_wall_ms": wall, "ms_per_frame": st_d.device_ms,
+                                 "note": "rtx_scene_create_ex(RTX_SCENE_DEVICE_BVH): Morton-order wide BVH built by kernels; identical traversal results, more node visits per ray than the host's binned-SAH tree (the default)"}
+            rd.close()
     extra = None
     if main:
         extra = (rm, render, pf, cam, cfg)

@@ -104,7 +104,7 @@ class RtxBvhInfo(C.Structure):
     _fields_ = [("n_nodes", C.c_uint32), ("n_triangles", C.c_uint32), ("n_items", C.c_uint32),
                 ("tlas_nodes", C.c_uint32), ("node_bytes", C.c_uint64), ("triangle_bytes", C.c_uint64),
                 ("item_bytes", C.c_uint64), ("texture_bytes", C.c_uint64), ("build_ms", C.c_float),
-                ("grouped_items", C.c_uint32), ("grouped_triangles", C.c_uint32), ("reserved", C.c_uint32)]
+                ("grouped_items", C.c_uint32), ("grouped_triangles", C.c_uint32), ("device_build_ms", C.c_float)]
 
 
 class RtxItemXform(C.Structure):
@@ -284,6 +284,7 @@ def bind(lib: C.CDLL, prefix: str = "rtx_") -> None:
     P = C.POINTER
     sig = {
         "scene_create": (C.c_int, [P(RtxSceneDesc), C.c_int, P(C.c_void_p)]),
+        "scene_create_ex": (C.c_int, [P(RtxSceneDesc), C.c_int, C.c_uint32, P(C.c_void_p)]),
         "scene_update_items": (C.c_int, [C.c_void_p, P(RtxItemXform), C.c_size_t]),
         "scene_set_lights": (C.c_int, [C.c_void_p, P(RtxLight), C.c_uint32]),
         "render_frame": (C.c_int, [C.c_void_p, P(RtxCamera), P(RtxConfig), C.c_void_p, C.c_void_p, C.c_void_p,
@@ -336,7 +337,7 @@ ABI_SYMBOLS = ["rtx_scene_create", "rtx_scene_update_items", "rtx_scene_set_ligh
                "rtx_scene_destroy", "rtx_last_error", "rtx_abi_version", "rtx_device_count",
                "rtx_post_process_device", "rtx_shadow_probe", "rtx_scene_create_multi", "rtx_scene_device_count",
                "rtx_gbuffer_create", "rtx_gbuffer_export", "rtx_gbuffer_open", "rtx_gbuffer_pointers", "rtx_gbuffer_download",
-               "rtx_gbuffer_destroy", "rtx_shard_unpack_all", "rtx_bandwidth_probe", "rtx_bvh_build_probe"]
+               "rtx_gbuffer_destroy", "rtx_shard_unpack_all", "rtx_bandwidth_probe", "rtx_bvh_build_probe", "rtx_scene_create_ex"]
 
 
 def fixture_path(name: str) -> str:

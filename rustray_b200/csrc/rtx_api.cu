@@ -41,6 +41,7 @@
 #include "../../include/rtx.h"
 #include "bvh_build.h"
 #include "rtx_kernels.cuh"
+#include "lbvh_build.cuh"
 
 using namespace rtx;
 
@@ -101,7 +102,7 @@ struct RtxScene {
     std::vector<RtxItem> src_items; std::vector<DItem> h_items; std::vector<RtxMaterial> src_mats;
     std::vector<uint32_t> mesh_root, mesh_tri_base; std::vector<RtxMesh> mesh_meta;
     uint32_t n_blas_nodes = 0, n_tris = 0, tlas_cap = 0, n_tlas_nodes = 0;
-    size_t texture_bytes = 0; float build_ms = 0.f;
+    size_t texture_bytes = 0; float build_ms = 0.f, device_build_ms = 0.f; uint32_t flags = 0;
     // device scene
     DevBuf<float4> nodes, tris; DevBuf<DItem> items; DevBuf<uint32_t> tlas_prims, fast_prims;
     uint32_t group_root = 0xFFFFFFFFu, n_fast_nodes = 0, n_group_tris = 0; std::vector<uint32_t> group_items;   // merged world-space BLAS
@@ -418,6 +419,12 @@ int rtx_sample_table(uint32_t samples, uint32_t* cell_size, uint16_t* xy) {
 }
 
 int rtx_scene_create(const RtxSceneDesc* d, int device, RtxScene** out) {
+    uint32_t flags = 0;
+    if (const char* e = getenv("RTX_DEVICE_BVH")) if (atoi(e) != 0) flags |= RTX_SCENE_DEVICE_BVH;
+    return rtx_scene_create_ex(d, device, flags, out);
+}
+
+int rtx_scene_create_ex(const RtxSceneDesc* d, int device, uint32_t scene_flags, RtxScene** out) {
     if (!d || !out) return fail(RTX_E_INVALID, "null argument");
     *out = nullptr;
     int ndev = 0;
@@ -426,8 +433,21 @@ int rtx_scene_create(const RtxSceneDesc* d, int device, RtxScene** out) {
     CU(cudaSetDevice(device));
     auto t0 = std::chrono::steady_clock::now();
     RtxScene* sc = new RtxScene();
-    sc->device = device;
+    sc->device = device; sc->flags = scene_flags;
     cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, device)); sc->sm_count = prop.multiProcessorCount;
+    const bool device_bvh = (scene_flags & RTX_SCENE_DEVICE_BVH) != 0;
+    // Morton-order wide BVH built by kernels (lbvh_build.cuh); a tree too deep for the traversal stack falls back to the host builder
+    auto build_boxes_on_device = [&](const std::vector<Aabb3>& boxes, WideBvh& bvh) -> bool {
+        lbvh::Box* d_boxes = nullptr;
+        if (cudaMalloc(&d_boxes, boxes.size() * sizeof(Aabb3)) != cudaSuccess) { cudaGetLastError(); return false; }
+        cudaMemcpy(d_boxes, boxes.data(), boxes.size() * sizeof(Aabb3), cudaMemcpyHostToDevice);
+        int deep = 0; float ms = 0.f;
+        const cudaError_t e = lbvh::build_on_device(d_boxes, (uint32_t)boxes.size(), bvh, kBlasDepthLimit, &deep, &ms);
+        cudaFree(d_boxes);
+        if (e != cudaSuccess) cudaGetLastError();
+        if (e == cudaSuccess && !deep) sc->device_build_ms += ms;
+        return e == cudaSuccess && !deep;
+    };
     auto bail = [&](int code, const std::string& m) { rtx_scene_destroy(sc); return fail(code, m); };
 
     // ---- validate + copy ----
@@ -470,14 +490,18 @@ int rtx_scene_create(const RtxSceneDesc* d, int device, RtxScene** out) {
         if (m.n_normals) h_nrms.insert(h_nrms.end(), m.normals, m.normals + 3 * (size_t)m.n_normals);
         if (m.n_normal_faces) h_nidx.insert(h_nidx.end(), m.normals_indices, m.normals_indices + 3 * (size_t)m.n_normal_faces);
     }
-    // BLAS builds are independent: one host thread per mesh, up to the hardware concurrency (config 5: 64 meshes of 156 k triangles)
+    // BLAS builds are independent: one host thread per mesh, up to the hardware concurrency (config 5: 64 meshes of 156 k triangles).
+    // With RTX_SCENE_DEVICE_BVH the threads only compute the triangle boxes and the trees are built by kernels, mesh after mesh.
     std::vector<WideBvh> bvhs(d->n_meshes);
     {
+        std::vector<std::vector<Aabb3>> mesh_boxes(device_bvh ? d->n_meshes : 0);
         std::atomic<uint32_t> next{0};
         auto work = [&]() {
+            std::vector<Aabb3> local;
             for (uint32_t mi = next.fetch_add(1); mi < d->n_meshes; mi = next.fetch_add(1)) {
                 const RtxMesh& m = d->meshes[mi]; MeshOff& o = moff[mi];
-                std::vector<Aabb3> boxes(m.n_faces);
+                std::vector<Aabb3>& boxes = device_bvh ? mesh_boxes[mi] : local;
+                boxes.resize(m.n_faces);
                 for (int k = 0; k < 3; k++) { o.lo[k] = INFINITY; o.hi[k] = -INFINITY; }
                 for (uint32_t f = 0; f < m.n_faces; f++) {
                     Aabb3& b = boxes[f];
@@ -488,7 +512,7 @@ int rtx_scene_create(const RtxSceneDesc* d, int device, RtxScene** out) {
                     }
                     for (int k = 0; k < 3; k++) { o.lo[k] = std::min(o.lo[k], b.lo[k]); o.hi[k] = std::max(o.hi[k], b.hi[k]); }   // TriMesh::aabb
                 }
-                build_wide_bvh(boxes.data(), m.n_faces, bvhs[mi], kBlasDepthLimit);
+                if (!device_bvh) build_wide_bvh(boxes.data(), m.n_faces, bvhs[mi], kBlasDepthLimit);
             }
         };
         const uint32_t nt = std::min<uint32_t>(d->n_meshes, std::max(1u, std::thread::hardware_concurrency()));
@@ -496,6 +520,11 @@ int rtx_scene_create(const RtxSceneDesc* d, int device, RtxScene** out) {
         for (uint32_t t = 1; t < nt; t++) pool.emplace_back(work);
         work();
         for (std::thread& t : pool) t.join();
+        if (device_bvh)
+            for (uint32_t mi = 0; mi < d->n_meshes; mi++) {
+                if (!build_boxes_on_device(mesh_boxes[mi], bvhs[mi])) build_wide_bvh(mesh_boxes[mi].data(), d->meshes[mi].n_faces, bvhs[mi], kBlasDepthLimit);
+                std::vector<Aabb3>().swap(mesh_boxes[mi]);
+            }
     }
     for (uint32_t mi = 0; mi < d->n_meshes; mi++) {
         const RtxMesh& m = d->meshes[mi]; const WideBvh& bvh = bvhs[mi];
@@ -560,7 +589,8 @@ int rtx_scene_create(const RtxSceneDesc* d, int device, RtxScene** out) {
                     p_item[k] = i; p_face[k] = f;
                 }
             }
-            WideBvh bvh; build_wide_bvh(boxes.data(), (uint32_t)gt, bvh, kBlasDepthLimit);
+            WideBvh bvh;
+            if (!device_bvh || !build_boxes_on_device(boxes, bvh)) build_wide_bvh(boxes.data(), (uint32_t)gt, bvh, kBlasDepthLimit);
             if (!(bvh.max_depth >= kStack - 2 || 2 * bvh.max_depth + 2 * 6 + 4 > kLaneStack)) {       // too deep: keep the per-item structure only
                 const uint32_t node_off = (uint32_t)(h_nodes.size() / 5), tri_off = (uint32_t)(h_tris.size() / 3);
                 append_nodes(h_nodes, bvh, node_off, tri_off);
@@ -748,6 +778,7 @@ int rtx_scene_bvh_info(const RtxScene* sc, RtxBvhInfo* info) {
     info->n_nodes = sc->n_blas_nodes; info->n_triangles = sc->n_tris; info->n_items = (uint32_t)sc->h_items.size();
     info->tlas_nodes = sc->n_tlas_nodes; info->node_bytes = (uint64_t)(sc->n_blas_nodes + sc->n_tlas_nodes + sc->n_fast_nodes) * 80;
     info->grouped_items = (uint32_t)sc->group_items.size(); info->grouped_triangles = sc->n_group_tris;
+    info->device_build_ms = sc->device_build_ms;
     info->triangle_bytes = (uint64_t)sc->n_tris * 48; info->item_bytes = sc->h_items.size() * sizeof(DItem);
     info->texture_bytes = sc->texture_bytes; info->build_ms = sc->build_ms;
     return RTX_OK;
@@ -1434,6 +1465,7 @@ int rtx_scene_create_multi(const RtxSceneDesc* d, const int* devices, uint32_t n
         r->mesh_tri_base = sc->mesh_tri_base; r->mesh_meta = sc->mesh_meta;
         r->n_blas_nodes = sc->n_blas_nodes; r->n_tris = sc->n_tris; r->tlas_cap = sc->tlas_cap; r->n_tlas_nodes = sc->n_tlas_nodes;
         r->texture_bytes = sc->texture_bytes; r->build_ms = sc->build_ms; r->n_enabled_lights = sc->n_enabled_lights;
+        r->device_build_ms = sc->device_build_ms; r->flags = sc->flags;
         r->group_root = sc->group_root; r->group_items = sc->group_items; r->n_group_tris = sc->n_group_tris; r->n_fast_nodes = sc->n_fast_nodes;
         const int s0 = devices[0];
         if ((rc = r->nodes.clone_from(sc->nodes, s0, dev)) || (rc = r->tris.clone_from(sc->tris, s0, dev)) || (rc = r->items.clone_from(sc->items, s0, dev)) ||

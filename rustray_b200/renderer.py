@@ -78,7 +78,7 @@ class Frame:
 class AbiRenderer:
     """Thin object wrapper over any library exporting the rtx ABI under `prefix`."""
 
-    def __init__(self, lib: C.CDLL, prefix: str, flat_scene: abi.FlatScene, device: int = 0, devices=None):
+    def __init__(self, lib: C.CDLL, prefix: str, flat_scene: abi.FlatScene, device: int = 0, devices=None, device_bvh: bool = False):
         """`devices`: list of CUDA ordinals -> one handle that renders every frame on all of them (rtx_scene_create_multi:
         scene replicated device-to-device, interleaved tiles, peer-memory stores into the first device's frame buffers)."""
         self._lib, self._p = lib, prefix
@@ -90,6 +90,8 @@ class AbiRenderer:
         if len(self.devices) > 1:
             arr = (C.c_int * len(self.devices))(*self.devices)
             rc = self._fn("scene_create_multi")(C.byref(desc), arr, len(self.devices), C.byref(self._h))
+        elif device_bvh:
+            rc = self._fn("scene_create_ex")(C.byref(desc), self.device, 1, C.byref(self._h))    # RTX_SCENE_DEVICE_BVH
         else:
             rc = self._fn("scene_create")(C.byref(desc), self.device, C.byref(self._h))
         self._check(rc)
@@ -180,8 +182,8 @@ def primary_ray(cam: abi.RtxCamera, x: int, y: int):
 class RendererManager(AbiRenderer):
     """B200 stand-in for reference `RendererManager` (src/renderer.rs:19-60)."""
 
-    def __init__(self, width: int, height: int, flat_scene: abi.FlatScene, device: int = 0, devices=None):
-        super().__init__(load_library(), "rtx_", flat_scene, device, devices)
+    def __init__(self, width: int, height: int, flat_scene: abi.FlatScene, device: int = 0, devices=None, device_bvh: bool = False):
+        super().__init__(load_library(), "rtx_", flat_scene, device, devices, device_bvh)
         self.width, self.height = width, height
         self.frame = Frame(width, height, pinned=True)
         self._done = False

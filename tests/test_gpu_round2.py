@@ -382,3 +382,94 @@ def test_two_ranks_render_into_rank0_over_cuda_ipc():
                         "--master-port", "29533", os.path.join(ROOT, "tools", "peer_frame_check.py")], cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-3000:])
     assert "PEER_FRAME_OK" in r.stdout and "NCCL_GATHER_OK" in r.stdout
+
+
+# ---- memory appetite -----------------------------------------------------------------------------
+def test_small_frames_allocate_small_queues_and_two_scenes_share_a_device():
+    """Queues are sized by the frame (a 800x600x1 frame must not reserve gigabytes), and two scene handles on one device render
+    interleaved without disturbing each other."""
+    import torch
+    fs1, cam1, cfg1 = abi.load_fixture("c1_spheres", samples=1, monte_carlo=0)
+    fs2, cam2, cfg2 = abi.load_fixture("kbert", samples=2, monte_carlo=1)
+    cam2 = abi.resize_camera(cam2, 480, 270)
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info(0)[0]
+    a = RendererManager(800, 600, fs1)
+    fa = a.start(cam1, cfg1)
+    used = free0 - torch.cuda.mem_get_info(0)[0]
+    assert used < 700 << 20, "config 1 (0.48 M primary rays) took %d MiB of device memory" % (used >> 20)
+    ia, ida = fa.image.copy(), fa.objects.copy()
+    b = RendererManager(480, 270, fs2)
+    fb = b.start(cam2, cfg2)
+    ib, idb = fb.image.copy(), fb.objects.copy()
+    for _ in range(2):                                                                           # interleave frames of the two handles
+        fa = a.start(cam1, cfg1); fb = b.start(cam2, cfg2)
+        assert np.array_equal(fa.objects, ida) and lsb_stats(fa.image, ia)[0] >= 0.9999
+        assert np.array_equal(fb.objects, idb) and lsb_stats(fb.image, ib)[0] >= 0.9999
+    # a bigger frame on the same handle grows the queues; a smaller one afterwards still works
+    big = a.render(abi.resize_camera(cam1, 1600, 1200), clone_cfg(cfg1, samples=4))               # (render() allocates a frame of the camera's size)
+    assert big.stats.primary_samples == 1600 * 1200 * 4
+    small = a.render(abi.resize_camera(cam1, 200, 150), cfg1)
+    assert small.stats.primary_samples == 200 * 150 and small.stats.host_syncs == 1
+    a.close(); b.close()
+
+
+# ---- BVH built on the device (SURVEY §8(f1), VERDICT r01 #9) -------------------------------------------------------------
+def _same_answers(fs, cam, cfg, w, h, rays):
+    host, dev = RendererManager(w, h, fs), RendererManager(w, h, fs, device_bvh=True)
+    assert dev.bvh_info().device_build_ms > 0.0 and host.bvh_info().device_build_ms == 0.0
+    o, d = rays
+    for kw in (dict(), dict(depth=2), dict(for_shadow=True), dict(for_shadow=True, stop_on_first_hit=True)):
+        assert host.trace(o, d, **kw).tobytes() == dev.trace(o, d, **kw).tobytes()              # the tree only prunes: identical hits, bit for bit
+    sa, sb = host.shadow_probe(o, d, 25.0), dev.shadow_probe(o, d, 25.0)
+    assert np.array_equal(sa["lit"], sb["lit"]) and np.array_equal(sa["k"], sb["k"], equal_nan=True)
+    fa, fb = host.start(cam, cfg), dev.start(cam, cfg)
+    assert np.array_equal(fa.objects, fb.objects) and np.array_equal(fa.depth, fb.depth) and lsb_stats(fa.image, fb.image)[0] >= 0.9999
+    assert (fa.stats.rays_closest, fa.stats.rays_shadow) == (fb.stats.rays_closest, fb.stats.rays_shadow)
+    return host, dev
+
+
+def test_device_built_bvh_gives_identical_results():
+    sc = synthetic.soup_scene(200_000, 150, cells=3, width=256, height=144)
+    fs, cam, cfg = scene_to_abi(sc, samples=1, monte_carlo=0)
+    host, dev = _same_answers(fs, cam, cfg, 256, 144, random_rays(6000, 9, center=(0, 0, 0), radius=90.0))
+    assert dev.bvh_info().grouped_triangles == 200_000                                            # the merged BLAS was built on the device too
+    oc = OracleRenderer(fs)
+    o, d = random_rays(3000, 10, center=(0, 0, 0), radius=90.0)
+    hg, hc = dev.trace(o, d), oc.trace(o, d)
+    assert np.array_equal(hg["item_index"], hc["item_index"]) and np.array_equal(hg["t"], hc["t"]) and np.array_equal(hg["face_id"], hc["face_id"])
+    fs, cam, cfg = abi.load_fixture("c2_floor_monkey", samples=2, monte_carlo=1)                 # transformed instance + a 2-triangle mesh
+    cam = abi.resize_camera(cam, 320, 180)
+    _same_answers(fs, cam, cfg, 320, 180, random_rays(4000, 3))
+    sc = synthetic.atrium_scene(160, 90, detail=0.03, tex_size=32, samples=1, monte_carlo=False)  # > 100 meshes of a few hundred triangles each
+    fs, cam, cfg = scene_to_abi(sc)
+    _same_answers(fs, cam, cfg, 160, 90, random_rays(4000, 6, center=(0, 4, 0), radius=9.0))
+
+
+def test_device_built_bvh_degenerate_meshes():
+    """1 / 2 / 3 / 4 / 9 triangles, coincident centroids (identical Morton codes), a flat mesh (zero extent on one axis)."""
+    from rustray_b200.scene_loader import Scene, Item, Material, Light, Camera, Config, SHAPE_MESH, LIGHT_POINT, mat_identity, mat_translation, to_radians
+    sc = Scene(".")
+    rng = np.random.default_rng(5)
+
+    def add(verts, idx, pos):
+        m = Material(id=sc.get_next_id(), name="m")
+        sc.materials.append(m)
+        sc.items.append(Item(id=sc.get_next_id(), name="it%d" % len(sc.items), shape=SHAPE_MESH, material=m, trans=mat_translation(*pos),
+                             mesh=synthetic._mesh(np.asarray(verts, dtype=np.float32), np.asarray(idx, dtype=np.uint32))))
+    tri = [[-1, -1, 0], [1, -1, 0], [0, 1, 0]]
+    for k, n in enumerate((1, 2, 3, 4, 9)):                                                        # n copies of one triangle: coincident centroids
+        v = np.concatenate([np.asarray(tri, dtype=np.float32) + np.float32([0, 0, 0.0]) for _ in range(n)])
+        add(v, np.arange(3 * n).reshape(-1, 3), (-8 + 4 * k, 0, -12))
+    g = 5                                                                                          # flat 5x5 grid (zero extent in y)
+    u, w_ = np.meshgrid(np.linspace(-2, 2, g + 1), np.linspace(-2, 2, g + 1), indexing="ij")
+    gv = np.stack([u, np.zeros_like(u), w_], -1).reshape(-1, 3)
+    gi = [[i * (g + 1) + j, (i + 1) * (g + 1) + j, (i + 1) * (g + 1) + j + 1] for i in range(g) for j in range(g)] + \
+         [[i * (g + 1) + j, (i + 1) * (g + 1) + j + 1, i * (g + 1) + j + 1] for i in range(g) for j in range(g)]
+    add(gv, gi, (0, -2.5, -12))
+    rv = rng.uniform(-1, 1, (300, 3)); add(rv, np.arange(300).reshape(-1, 3), (0, 4, -14))      # 100 random triangles
+    sc.lights.append(Light(sc.get_next_id(), "l", np.float32([0, 10, -4]), np.float32([0, -1, 0]), np.float32([1, 1, 1]), 300.0, 1.5, LIGHT_POINT))
+    sc.cam = Camera(); sc.cam.fov = to_radians(70.0); sc.cam.init(192, 128)
+    sc.config = Config()
+    fs, cam, cfg = scene_to_abi(sc)
+    _same_answers(fs, cam, cfg, 192, 128, random_rays(5000, 2, center=(0, 0, -12), radius=14.0))
