@@ -225,70 +225,88 @@ __global__ void collapse_kernel(const Task* __restrict__ tasks, uint32_t n_tasks
     out_nodes[task.wide] = w;
 }
 
+// Scratch memory of the builder, grown on demand and reused from mesh to mesh (a scene of 64 meshes would otherwise pay 64 x 17
+// cudaMalloc / cudaFree pairs, each a device synchronisation).
+struct Workspace {
+    size_t cap = 0, tmp_bytes = 0;
+    uint64_t *keys = nullptr, *keys2 = nullptr; uint32_t *vals = nullptr, *vals2 = nullptr, *bounds = nullptr, *arrived = nullptr, *counters = nullptr, *prim_order = nullptr;
+    int *left = nullptr, *right = nullptr, *parent = nullptr; uint2* range = nullptr; Box *node_box = nullptr, *boxes = nullptr; void* tmp = nullptr;
+    WideNode* nodes = nullptr; struct TaskT { uint32_t wide; int node2; uint32_t depth; }; void* tq[2] = {nullptr, nullptr};
+    void release() {
+        cudaFree(keys); cudaFree(keys2); cudaFree(vals); cudaFree(vals2); cudaFree(bounds); cudaFree(arrived); cudaFree(counters); cudaFree(prim_order);
+        cudaFree(left); cudaFree(right); cudaFree(parent); cudaFree(range); cudaFree(node_box); cudaFree(boxes); cudaFree(nodes); cudaFree(tq[0]); cudaFree(tq[1]); cudaFree(tmp);
+        *this = Workspace();
+    }
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        release();
+        cudaError_t e;
+#define WS(p, bytes) if ((e = cudaMalloc((void**)&p, (bytes))) != cudaSuccess) { release(); return e; }
+        WS(keys, n * 8) WS(keys2, n * 8) WS(vals, n * 4) WS(vals2, n * 4) WS(bounds, 6 * 4) WS(arrived, n * 4) WS(counters, 8 * 4) WS(prim_order, n * 4)
+        WS(left, n * 4) WS(right, n * 4) WS(parent, 2 * n * 4) WS(range, n * 8) WS(node_box, n * sizeof(Box)) WS(boxes, n * sizeof(Box)) WS(nodes, (n + 8) * sizeof(WideNode))
+        WS(tq[0], n * 12) WS(tq[1], n * 12)
+        if ((e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, vals, vals2, (int)n, 0, 63)) != cudaSuccess) { release(); return e; }
+        WS(tmp, tmp_bytes)
+#undef WS
+        cap = n;
+        return cudaSuccess;
+    }
+};
+
 // Host driver.  d_boxes: n boxes on the current device.  Results are copied into `out` (host): the scene assembly of
 // rtx_scene_create (node / primitive index offsets, triangle packing) is shared with the host builder.
 // Returns cudaSuccess or the first CUDA error; *deep = 1 when the Morton tree does not fit `depth_limit` levels.
-inline cudaError_t build_on_device(const Box* d_boxes, uint32_t n, WideBvh& out, int depth_limit, int* deep, float* device_ms) {
+inline cudaError_t build_on_device(Workspace& W, const Box* h_boxes, uint32_t n, WideBvh& out, int depth_limit, int* deep, float* device_ms) {
     out.nodes.clear(); out.prim_order.clear(); out.max_depth = 0;
     if (deep) *deep = 0;
     if (n == 0) return cudaSuccess;
-    cudaError_t e = cudaSuccess;
-#define LB(x) do { e = (x); if (e != cudaSuccess) goto done; } while (0)
-    uint64_t *keys = nullptr, *keys2 = nullptr; uint32_t *vals = nullptr, *vals2 = nullptr, *bounds = nullptr, *arrived = nullptr, *counters = nullptr, *prim_order = nullptr;
-    int *left = nullptr, *right = nullptr, *parent = nullptr; uint2* range = nullptr; Box* node_box = nullptr; void* tmp = nullptr; size_t tmp_bytes = 0;
-    WideNode* nodes = nullptr; Task *tq[2] = {nullptr, nullptr};
+    cudaError_t e = W.reserve(n);
+    if (e != cudaSuccess) return e;
+    static_assert(sizeof(Task) == 12, "task size");
+    Task* tq[2] = {(Task*)W.tq[0], (Task*)W.tq[1]};
     const uint32_t node_cap = n + 8;                                    // every wide node but the root is an internal binary node: <= n - 1
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    LB(cudaMalloc(&keys, (size_t)n * 8)); LB(cudaMalloc(&keys2, (size_t)n * 8)); LB(cudaMalloc(&vals, (size_t)n * 4)); LB(cudaMalloc(&vals2, (size_t)n * 4));
-    LB(cudaMalloc(&bounds, 6 * 4)); LB(cudaMalloc(&arrived, (size_t)n * 4)); LB(cudaMalloc(&counters, 8 * 4)); LB(cudaMalloc(&prim_order, (size_t)n * 4));
-    LB(cudaMalloc(&left, (size_t)n * 4)); LB(cudaMalloc(&right, (size_t)n * 4)); LB(cudaMalloc(&parent, (size_t)2 * n * 4)); LB(cudaMalloc(&range, (size_t)n * 8));
-    LB(cudaMalloc(&node_box, (size_t)n * sizeof(Box))); LB(cudaMalloc(&nodes, (size_t)node_cap * sizeof(WideNode)));
-    LB(cudaMalloc(&tq[0], (size_t)n * sizeof(Task))); LB(cudaMalloc(&tq[1], (size_t)n * sizeof(Task)));
+    uint32_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define LB(x) do { e = (x); if (e != cudaSuccess) goto done; } while (0)
+    LB(cudaMemcpy(W.boxes, h_boxes, (size_t)n * sizeof(Box), cudaMemcpyHostToDevice));
     cudaEventRecord(e0);
     {
         const uint32_t init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
-        LB(cudaMemcpy(bounds, init, sizeof(init), cudaMemcpyHostToDevice));
-        bounds_kernel<<<148 * 4, 256>>>(d_boxes, n, bounds);
-        morton_kernel<<<(n + 255) / 256, 256>>>(d_boxes, n, bounds, keys, vals);
-        LB(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, vals, vals2, (int)n, 0, 63));
-        LB(cudaMalloc(&tmp, tmp_bytes));
-        LB(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, vals, vals2, (int)n, 0, 63));
-        LB(cudaMemset(arrived, 0, (size_t)n * 4)); LB(cudaMemset(counters, 0, 8 * 4));
+        LB(cudaMemcpy(W.bounds, init, sizeof(init), cudaMemcpyHostToDevice));
+        bounds_kernel<<<148 * 4, 256>>>(W.boxes, n, W.bounds);
+        morton_kernel<<<(n + 255) / 256, 256>>>(W.boxes, n, W.bounds, W.keys, W.vals);
+        size_t tb = W.tmp_bytes;
+        LB(cub::DeviceRadixSort::SortPairs(W.tmp, tb, W.keys, W.keys2, W.vals, W.vals2, (int)n, 0, 63));
+        LB(cudaMemsetAsync(W.arrived, 0, (size_t)n * 4)); LB(cudaMemsetAsync(W.counters, 0, 8 * 4));
         if (n > 1) {
-            radix_tree_kernel<<<(n - 1 + 255) / 256, 256>>>(keys2, (int)n, left, right, parent, range);
-            fit_kernel<<<(n + 255) / 256, 256>>>(d_boxes, vals2, (int)n, left, right, parent, node_box, arrived);
+            radix_tree_kernel<<<(n - 1 + 255) / 256, 256>>>(W.keys2, (int)n, W.left, W.right, W.parent, W.range);
+            fit_kernel<<<(n + 255) / 256, 256>>>(W.boxes, W.vals2, (int)n, W.left, W.right, W.parent, W.node_box, W.arrived);
         }
         // root task, then one launch per level of the wide tree
         const Task root{0u, n > 1 ? 0 : ~0, 1u};
         LB(cudaMemcpy(tq[0], &root, sizeof(root), cudaMemcpyHostToDevice));
         const uint32_t one = 1u;
-        LB(cudaMemcpy(counters + 0, &one, 4, cudaMemcpyHostToDevice));  // node 0 = root
+        LB(cudaMemcpy(W.counters + 0, &one, 4, cudaMemcpyHostToDevice));  // node 0 = root
         uint32_t n_tasks = 1; int cur = 0;
         for (int level = 0; n_tasks > 0 && level < 4096; level++) {
-            LB(cudaMemset(counters + 2, 0, 4));
-            collapse_kernel<<<(n_tasks + 127) / 128, 128>>>(tq[cur], n_tasks, left, right, range, node_box, d_boxes, vals2, nodes, node_cap, prim_order, counters, tq[cur ^ 1]);
-            LB(cudaMemcpy(&n_tasks, counters + 2, 4, cudaMemcpyDeviceToHost));
+            LB(cudaMemsetAsync(W.counters + 2, 0, 4));
+            collapse_kernel<<<(n_tasks + 127) / 128, 128>>>(tq[cur], n_tasks, W.left, W.right, W.range, W.node_box, W.boxes, W.vals2, W.nodes, node_cap, W.prim_order, W.counters, tq[cur ^ 1]);
+            LB(cudaMemcpy(&n_tasks, W.counters + 2, 4, cudaMemcpyDeviceToHost));
             cur ^= 1;
         }
     }
     cudaEventRecord(e1);
-    {
-        uint32_t h[8];
-        LB(cudaMemcpy(h, counters, sizeof(h), cudaMemcpyDeviceToHost));
-        if (h[4]) { e = cudaErrorUnknown; goto done; }
-        out.max_depth = (int)h[3];
-        if (depth_limit > 0 && out.max_depth > depth_limit) { if (deep) *deep = 1; goto done; }
-        out.nodes.resize(h[0]); out.prim_order.resize(n);
-        LB(cudaMemcpy(out.nodes.data(), nodes, (size_t)h[0] * sizeof(WideNode), cudaMemcpyDeviceToHost));
-        LB(cudaMemcpy(out.prim_order.data(), prim_order, (size_t)n * 4, cudaMemcpyDeviceToHost));
-        if (h[1] != n) { e = cudaErrorUnknown; goto done; }
-        if (device_ms) cudaEventElapsedTime(device_ms, e0, e1);
-    }
+    LB(cudaMemcpy(h, W.counters, sizeof(h), cudaMemcpyDeviceToHost));
+    if (h[4] || h[1] != n) { e = cudaErrorUnknown; goto done; }
+    out.max_depth = (int)h[3];
+    if (depth_limit > 0 && out.max_depth > depth_limit) { if (deep) *deep = 1; goto done; }
+    out.nodes.resize(h[0]); out.prim_order.resize(n);
+    LB(cudaMemcpy(out.nodes.data(), W.nodes, (size_t)h[0] * sizeof(WideNode), cudaMemcpyDeviceToHost));
+    LB(cudaMemcpy(out.prim_order.data(), W.prim_order, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    if (device_ms) cudaEventElapsedTime(device_ms, e0, e1);
 done:
 #undef LB
-    cudaFree(keys); cudaFree(keys2); cudaFree(vals); cudaFree(vals2); cudaFree(bounds); cudaFree(arrived); cudaFree(counters); cudaFree(prim_order);
-    cudaFree(left); cudaFree(right); cudaFree(parent); cudaFree(range); cudaFree(node_box); cudaFree(nodes); cudaFree(tq[0]); cudaFree(tq[1]); cudaFree(tmp);
     if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1);
     return e;
 }

@@ -432,18 +432,21 @@ int rtx_scene_create_ex(const RtxSceneDesc* d, int device, uint32_t scene_flags,
     if (device < 0 || device >= ndev) return fail(RTX_E_INVALID, "bad device ordinal");
     CU(cudaSetDevice(device));
     auto t0 = std::chrono::steady_clock::now();
+    const bool trace_build = getenv("RTX_TRACE_BUILD") != nullptr;
+    auto phase = [&](const char* what) {
+        if (trace_build) fprintf(stderr, "[build] %8.1f ms  %s\n", std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count(), what);
+    };
     RtxScene* sc = new RtxScene();
     sc->device = device; sc->flags = scene_flags;
     cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, device)); sc->sm_count = prop.multiProcessorCount;
     const bool device_bvh = (scene_flags & RTX_SCENE_DEVICE_BVH) != 0;
     // Morton-order wide BVH built by kernels (lbvh_build.cuh); a tree too deep for the traversal stack falls back to the host builder
+    lbvh::Workspace lbvh_ws;
+    struct WsGuard { lbvh::Workspace& w; ~WsGuard() { w.release(); } } ws_guard{lbvh_ws};
     auto build_boxes_on_device = [&](const std::vector<Aabb3>& boxes, WideBvh& bvh) -> bool {
-        lbvh::Box* d_boxes = nullptr;
-        if (cudaMalloc(&d_boxes, boxes.size() * sizeof(Aabb3)) != cudaSuccess) { cudaGetLastError(); return false; }
-        cudaMemcpy(d_boxes, boxes.data(), boxes.size() * sizeof(Aabb3), cudaMemcpyHostToDevice);
         int deep = 0; float ms = 0.f;
-        const cudaError_t e = lbvh::build_on_device(d_boxes, (uint32_t)boxes.size(), bvh, kBlasDepthLimit, &deep, &ms);
-        cudaFree(d_boxes);
+        static_assert(sizeof(lbvh::Box) == sizeof(Aabb3), "box layout");
+        const cudaError_t e = lbvh::build_on_device(lbvh_ws, reinterpret_cast<const lbvh::Box*>(boxes.data()), (uint32_t)boxes.size(), bvh, kBlasDepthLimit, &deep, &ms);
         if (e != cudaSuccess) cudaGetLastError();
         if (e == cudaSuccess && !deep) sc->device_build_ms += ms;
         return e == cudaSuccess && !deep;
@@ -467,29 +470,44 @@ int rtx_scene_create_ex(const RtxSceneDesc* d, int device, uint32_t scene_flags,
     sc->src_mats.assign(d->materials, d->materials + d->n_materials);
 
     // ---- meshes: BLAS per mesh ----
+    // The shading-side mesh arrays (vertices, indices, uvs, normals and their index lists) go straight from the caller's memory
+    // into their place in the device arrays: no host-side concatenation (config 5: 480 MB).
     std::vector<float4> h_nodes, h_tris;
-    std::vector<float> h_verts, h_uvs, h_nrms; std::vector<uint32_t> h_idx, h_uvidx, h_nidx;
     struct MeshOff { uint32_t vert, idx, uv, uvidx, nrm, nidx; float lo[3], hi[3]; };
     std::vector<MeshOff> moff(d->n_meshes);
     sc->mesh_root.resize(d->n_meshes); sc->mesh_tri_base.resize(d->n_meshes);
     sc->mesh_meta.assign(d->meshes, d->meshes + d->n_meshes);
-    for (uint32_t mi = 0; mi < d->n_meshes; mi++) {
-        const RtxMesh& m = d->meshes[mi];
-        if (m.n_faces == 0) return bail(RTX_E_EMPTY_MESH, "mesh with 0 triangles (parry TriMesh::new panics)");
-        for (size_t k = 0; k < 3 * (size_t)m.n_faces; k++) if (m.indices[k] >= m.n_vertices) return bail(RTX_E_INVALID, "vertex index out of range");
-        for (size_t k = 0; k < 3 * (size_t)m.n_uv_faces; k++) if (m.uv_indices[k] >= m.n_uvs) return bail(RTX_E_INVALID, "uv index out of range");
-        for (size_t k = 0; k < 3 * (size_t)m.n_normal_faces; k++) if (m.normals_indices[k] >= m.n_normals) return bail(RTX_E_INVALID, "normal index out of range");
-        if (m.n_normal_faces && m.n_normal_faces < m.n_faces) return bail(RTX_E_INVALID, "normals_indices shorter than indices");
-        MeshOff& o = moff[mi];
-        o.vert = (uint32_t)h_verts.size(); o.idx = (uint32_t)h_idx.size(); o.uv = (uint32_t)h_uvs.size();
-        o.uvidx = (uint32_t)h_uvidx.size(); o.nrm = (uint32_t)h_nrms.size(); o.nidx = (uint32_t)h_nidx.size();
-        h_verts.insert(h_verts.end(), m.vertices, m.vertices + 3 * (size_t)m.n_vertices);
-        h_idx.insert(h_idx.end(), m.indices, m.indices + 3 * (size_t)m.n_faces);
-        if (m.n_uvs) h_uvs.insert(h_uvs.end(), m.uvs, m.uvs + 2 * (size_t)m.n_uvs);
-        if (m.n_uv_faces) h_uvidx.insert(h_uvidx.end(), m.uv_indices, m.uv_indices + 3 * (size_t)m.n_uv_faces);
-        if (m.n_normals) h_nrms.insert(h_nrms.end(), m.normals, m.normals + 3 * (size_t)m.n_normals);
-        if (m.n_normal_faces) h_nidx.insert(h_nidx.end(), m.normals_indices, m.normals_indices + 3 * (size_t)m.n_normal_faces);
+    {
+        uint64_t tv = 0, ti = 0, tu = 0, tui = 0, tn = 0, tni = 0;        // element counts (floats / uint32s)
+        for (uint32_t mi = 0; mi < d->n_meshes; mi++) {
+            const RtxMesh& m = d->meshes[mi];
+            if (m.n_faces == 0) return bail(RTX_E_EMPTY_MESH, "mesh with 0 triangles (parry TriMesh::new panics)");
+            if (m.n_normal_faces && m.n_normal_faces < m.n_faces) return bail(RTX_E_INVALID, "normals_indices shorter than indices");
+            MeshOff& o = moff[mi];
+            o.vert = (uint32_t)tv; o.idx = (uint32_t)ti; o.uv = (uint32_t)tu; o.uvidx = (uint32_t)tui; o.nrm = (uint32_t)tn; o.nidx = (uint32_t)tni;
+            tv += 3 * (uint64_t)m.n_vertices; ti += 3 * (uint64_t)m.n_faces; tu += 2 * (uint64_t)m.n_uvs; tui += 3 * (uint64_t)m.n_uv_faces;
+            tn += 3 * (uint64_t)m.n_normals; tni += 3 * (uint64_t)m.n_normal_faces;
+            if (tv > 0xffffffffull || ti > 0xffffffffull || tu > 0xffffffffull || tui > 0xffffffffull || tn > 0xffffffffull || tni > 0xffffffffull)
+                return bail(RTX_E_INVALID, "mesh arrays exceed 2^32 elements");
+        }
+        int rc0;
+        if ((rc0 = sc->verts.alloc(std::max<uint64_t>(tv, 1))) || (rc0 = sc->idx.alloc(std::max<uint64_t>(ti, 1))) || (rc0 = sc->uvs.alloc(std::max<uint64_t>(tu, 1))) ||
+            (rc0 = sc->uv_idx.alloc(std::max<uint64_t>(tui, 1))) || (rc0 = sc->nrms.alloc(std::max<uint64_t>(tn, 1))) || (rc0 = sc->n_idx.alloc(std::max<uint64_t>(tni, 1)))) {
+            std::string keep = g_err; rtx_scene_destroy(sc); g_err = keep; return rc0;
+        }
+        for (uint32_t mi = 0; mi < d->n_meshes; mi++) {
+            const RtxMesh& m = d->meshes[mi]; const MeshOff& o = moff[mi];
+            cudaMemcpyAsync(sc->verts.p + o.vert, m.vertices, 12 * (size_t)m.n_vertices, cudaMemcpyHostToDevice, 0);
+            cudaMemcpyAsync(sc->idx.p + o.idx, m.indices, 12 * (size_t)m.n_faces, cudaMemcpyHostToDevice, 0);
+            if (m.n_uvs) cudaMemcpyAsync(sc->uvs.p + o.uv, m.uvs, 8 * (size_t)m.n_uvs, cudaMemcpyHostToDevice, 0);
+            if (m.n_uv_faces) cudaMemcpyAsync(sc->uv_idx.p + o.uvidx, m.uv_indices, 12 * (size_t)m.n_uv_faces, cudaMemcpyHostToDevice, 0);
+            if (m.n_normals) cudaMemcpyAsync(sc->nrms.p + o.nrm, m.normals, 12 * (size_t)m.n_normals, cudaMemcpyHostToDevice, 0);
+            if (m.n_normal_faces) cudaMemcpyAsync(sc->n_idx.p + o.nidx, m.normals_indices, 12 * (size_t)m.n_normal_faces, cudaMemcpyHostToDevice, 0);
+        }
+        if (cudaGetLastError() != cudaSuccess) return bail(RTX_E_CUDA, "mesh array upload failed");
     }
+    std::atomic<int> bad_index{0};                                        // 1 vertex, 2 uv, 3 normal index out of range (checked by the worker threads below)
+    phase("mesh arrays uploaded");
     // BLAS builds are independent: one host thread per mesh, up to the hardware concurrency (config 5: 64 meshes of 156 k triangles).
     // With RTX_SCENE_DEVICE_BVH the threads only compute the triangle boxes and the trees are built by kernels, mesh after mesh.
     std::vector<WideBvh> bvhs(d->n_meshes);
@@ -500,6 +518,15 @@ int rtx_scene_create_ex(const RtxSceneDesc* d, int device, uint32_t scene_flags,
             std::vector<Aabb3> local;
             for (uint32_t mi = next.fetch_add(1); mi < d->n_meshes; mi = next.fetch_add(1)) {
                 const RtxMesh& m = d->meshes[mi]; MeshOff& o = moff[mi];
+                {
+                    bool ok = true;
+                    for (size_t k = 0; k < 3 * (size_t)m.n_faces; k++) ok &= m.indices[k] < m.n_vertices;
+                    if (!ok) { bad_index.store(1); continue; }
+                    for (size_t k = 0; k < 3 * (size_t)m.n_uv_faces; k++) ok &= m.uv_indices[k] < m.n_uvs;
+                    if (!ok) { bad_index.store(2); continue; }
+                    for (size_t k = 0; k < 3 * (size_t)m.n_normal_faces; k++) ok &= m.normals_indices[k] < m.n_normals;
+                    if (!ok) { bad_index.store(3); continue; }
+                }
                 std::vector<Aabb3>& boxes = device_bvh ? mesh_boxes[mi] : local;
                 boxes.resize(m.n_faces);
                 for (int k = 0; k < 3; k++) { o.lo[k] = INFINITY; o.hi[k] = -INFINITY; }
@@ -520,30 +547,63 @@ int rtx_scene_create_ex(const RtxSceneDesc* d, int device, uint32_t scene_flags,
         for (uint32_t t = 1; t < nt; t++) pool.emplace_back(work);
         work();
         for (std::thread& t : pool) t.join();
+        if (bad_index.load()) return bail(RTX_E_INVALID, bad_index.load() == 1 ? "vertex index out of range" : bad_index.load() == 2 ? "uv index out of range" : "normal index out of range");
+        phase(device_bvh ? "indices checked, triangle boxes" : "indices checked, triangle boxes + host BLAS builds");
+        if (device_bvh) {
+            uint32_t max_faces = 0;
+            for (uint32_t mi = 0; mi < d->n_meshes; mi++) max_faces = std::max(max_faces, d->meshes[mi].n_faces);
+            lbvh_ws.reserve(max_faces);                                   // one allocation for the largest mesh, reused by all
+        }
         if (device_bvh)
             for (uint32_t mi = 0; mi < d->n_meshes; mi++) {
                 if (!build_boxes_on_device(mesh_boxes[mi], bvhs[mi])) build_wide_bvh(mesh_boxes[mi].data(), d->meshes[mi].n_faces, bvhs[mi], kBlasDepthLimit);
                 std::vector<Aabb3>().swap(mesh_boxes[mi]);
             }
     }
-    for (uint32_t mi = 0; mi < d->n_meshes; mi++) {
-        const RtxMesh& m = d->meshes[mi]; const WideBvh& bvh = bvhs[mi];
-        if (bvh.max_depth >= kStack - 2 || 2 * bvh.max_depth + 2 * 6 + 4 > kLaneStack) return bail(RTX_E_INVALID, "BLAS too deep for the traversal stack");
-        const uint32_t node_off = (uint32_t)(h_nodes.size() / 5), tri_off = (uint32_t)(h_tris.size() / 3);
-        sc->mesh_root[mi] = node_off; sc->mesh_tri_base[mi] = tri_off;
-        append_nodes(h_nodes, bvh, node_off, tri_off);
-        for (uint32_t f : bvh.prim_order) {
-            const float* a = m.vertices + 3 * (size_t)m.indices[3 * (size_t)f];
-            const float* b = m.vertices + 3 * (size_t)m.indices[3 * (size_t)f + 1];
-            const float* c = m.vertices + 3 * (size_t)m.indices[3 * (size_t)f + 2];
-            float fb; memcpy(&fb, &f, 4);
-            h_tris.push_back(make_float4(a[0], a[1], a[2], fb));
-            h_tris.push_back(make_float4(b[0], b[1], b[2], 0.f));
-            h_tris.push_back(make_float4(c[0], c[1], c[2], 0.f));
+    if (device_bvh) phase("device BLAS builds");
+    {
+        // node / triangle offsets per mesh, then the meshes are packed side by side by a pool of threads (30 M float4 for config 5)
+        std::vector<uint32_t> node_off(d->n_meshes + 1, 0), tri_off(d->n_meshes + 1, 0);
+        for (uint32_t mi = 0; mi < d->n_meshes; mi++) {
+            const WideBvh& bvh = bvhs[mi];
+            if (bvh.max_depth >= kStack - 2 || 2 * bvh.max_depth + 2 * 6 + 4 > kLaneStack) return bail(RTX_E_INVALID, "BLAS too deep for the traversal stack");
+            node_off[mi + 1] = node_off[mi] + (uint32_t)bvh.nodes.size(); tri_off[mi + 1] = tri_off[mi] + (uint32_t)bvh.prim_order.size();
+            sc->mesh_root[mi] = node_off[mi]; sc->mesh_tri_base[mi] = tri_off[mi];
         }
-        bvhs[mi] = WideBvh();                                             // release as we go
+        h_nodes.reserve(((size_t)node_off[d->n_meshes] + 2 * (size_t)d->n_items + 64) * 5);    // room for the TLASes (a merged BLAS may still reallocate)
+        h_nodes.resize((size_t)node_off[d->n_meshes] * 5); h_tris.resize((size_t)tri_off[d->n_meshes] * 3);
+        std::atomic<uint32_t> next{0};
+        auto pack = [&]() {
+            for (uint32_t mi = next.fetch_add(1); mi < d->n_meshes; mi = next.fetch_add(1)) {
+                const RtxMesh& m = d->meshes[mi]; WideBvh& bvh = bvhs[mi];
+                float4* np = h_nodes.data() + (size_t)node_off[mi] * 5;
+                for (size_t k = 0; k < bvh.nodes.size(); k++) {
+                    WideNode n = bvh.nodes[k];
+                    n.child_base += node_off[mi]; n.prim_base += tri_off[mi];
+                    memcpy(np + 5 * k, &n, 80);
+                }
+                float4* tp = h_tris.data() + (size_t)tri_off[mi] * 3;
+                for (size_t k = 0; k < bvh.prim_order.size(); k++) {
+                    const uint32_t f = bvh.prim_order[k];
+                    const float* a = m.vertices + 3 * (size_t)m.indices[3 * (size_t)f];
+                    const float* b = m.vertices + 3 * (size_t)m.indices[3 * (size_t)f + 1];
+                    const float* c = m.vertices + 3 * (size_t)m.indices[3 * (size_t)f + 2];
+                    float fb; memcpy(&fb, &f, 4);
+                    tp[3 * k] = make_float4(a[0], a[1], a[2], fb);
+                    tp[3 * k + 1] = make_float4(b[0], b[1], b[2], 0.f);
+                    tp[3 * k + 2] = make_float4(c[0], c[1], c[2], 0.f);
+                }
+                bvh = WideBvh();                                              // release as we go
+            }
+        };
+        const uint32_t nt = std::min<uint32_t>(d->n_meshes, std::max(1u, std::thread::hardware_concurrency()));
+        std::vector<std::thread> pool;
+        for (uint32_t t = 1; t < nt; t++) pool.emplace_back(pack);
+        if (d->n_meshes) pack();
+        for (std::thread& t : pool) t.join();
     }
     sc->n_blas_nodes = (uint32_t)(h_nodes.size() / 5); sc->n_tris = (uint32_t)(h_tris.size() / 3);
+    phase("BLAS nodes + triangles assembled");
 
     // ---- items ----
     sc->h_items.resize(d->n_items);
@@ -611,6 +671,7 @@ int rtx_scene_create_ex(const RtxSceneDesc* d, int device, uint32_t scene_flags,
         }
     }
 
+    phase("merged BLAS");
     // ---- TLASes: the full one (every item) and the fast one (ungrouped items + the merged BLAS); space reserved for updates ----
     std::vector<float4> tlas_nodes, fast_nodes; std::vector<uint32_t> tlas_prims, fast_prims;
     sc->tlas_cap = std::max<uint32_t>(8, d->n_items + 1);
@@ -653,15 +714,16 @@ int rtx_scene_create_ex(const RtxSceneDesc* d, int device, uint32_t scene_flags,
     }
     std::vector<DLight> h_lights; fill_lights(d->lights, d->n_lights, h_lights);
 
+    phase("TLAS, materials, textures");
     // ---- upload ----
     int rc;
     if ((rc = sc->nodes.upload(h_nodes)) || (rc = sc->tris.upload(h_tris)) || (rc = sc->items.upload(sc->h_items)) ||
-        (rc = sc->tlas_prims.upload(tlas_prims)) || (rc = sc->fast_prims.upload(fast_prims)) || (rc = sc->verts.upload(h_verts)) || (rc = sc->idx.upload(h_idx)) ||
-        (rc = sc->uvs.upload(h_uvs)) || (rc = sc->uv_idx.upload(h_uvidx)) || (rc = sc->nrms.upload(h_nrms)) || (rc = sc->n_idx.upload(h_nidx)) ||
+        (rc = sc->tlas_prims.upload(tlas_prims)) || (rc = sc->fast_prims.upload(fast_prims)) ||
         (rc = sc->mats.upload(h_mats)) || (rc = sc->texs.upload(h_texs)) || (rc = sc->texels.upload(h_texels)) || (rc = sc->lights.upload(h_lights))) {
         std::string keep = g_err; rtx_scene_destroy(sc); g_err = keep; return rc;
     }
     CU(cudaDeviceSynchronize());
+    phase("uploaded");
     refresh_dev(*sc);
     sc->dev.n_lights = d->n_lights;
     sc->n_enabled_lights = 0;
