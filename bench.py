@@ -290,7 +290,7 @@ def measure_workload(H, name, steps, warmup, with_cpu, peak, peak_src, l2_gbs, t
         return st
 
     # ---- stats frame (untimed): counted traversal work for the roofline ----
-    cfg_stats = abi.RtxConfig(); C.memmove(C.byref(cfg_stats), C.byref(cfg), C.sizeof(cfg)); cfg_stats.debug_flags = 1
+    cfg_stats = abi.RtxConfig(); C.memmove(C.byref(cfg_stats), C.byref(cfg), C.sizeof(cfg)); cfg_stats.debug_flags = 1 | 8
     st0 = render(cfg_stats)
     for _ in range(warmup):
         render(cfg); pf.finish()
@@ -315,6 +315,16 @@ def measure_workload(H, name, steps, warmup, with_cpu, peak, peak_src, l2_gbs, t
         closest_ms += st.closest_ms; shadow_ms += st.shadow_ms; waves += st.waves; syncs += st.host_syncs
     H.barrier()
     clk = clocks.stop() if H.rank == 0 else None
+    # ---- per-kernel durations for the roofline: in the product schedule the shadow kernels of wave k overlap the closest-hit / shade
+    # kernels of wave k+1 on a second stream, so their CUDA-event times are not exclusive.  The same frames are therefore run once
+    # more with the two streams serialised (RTX_DEBUG_SERIAL_STREAMS); `value` / `e2e` above and below use the overlapped schedule.
+    cfg_serial = abi.RtxConfig(); C.memmove(C.byref(cfg_serial), C.byref(cfg), C.sizeof(cfg)); cfg_serial.debug_flags = 8
+    overlapped = {"closest_ms_per_frame": closest_ms / steps, "shadow_ms_per_frame": shadow_ms / steps}
+    closest_ms, shadow_ms, waves, serial_ms = 0.0, 0.0, 0, 0.0
+    n_serial = max(1, min(steps, 5))
+    for _ in range(n_serial):
+        st = render(cfg_serial); pf.finish()
+        closest_ms += st.closest_ms; shadow_ms += st.shadow_ms; waves += st.waves; serial_ms += st.device_ms
     rays_all = H.allsum(rays)
     launches_all = H.allsum(launches)
     slowest_rank_ms = H.allmax(rank_ms / steps)
@@ -352,15 +362,17 @@ def measure_workload(H, name, steps, warmup, with_cpu, peak, peak_src, l2_gbs, t
         t = traffic_db.get(name)
         if t and traffic_db.get("source_sha") == source_sha():
             dom_traffic = t
-        rf = roofline_block(st0, closest_ms, shadow_ms, rank_ms, steps, waves, rays / steps, peak, peak_src, l2_gbs,
+        rf = roofline_block(st0, closest_ms, shadow_ms, serial_ms, n_serial, waves, rays / steps, peak, peak_src, l2_gbs,
                             clk["sm_mhz"] if clk else None, prop.multi_processor_count, info.node_bytes + info.triangle_bytes,
                             (dom_traffic or {}).get("dram_bytes_per_launch"))
+        rf["kernel_times"] = {"source": "%d frames with the shadow stream serialised (RTX_DEBUG_SERIAL_STREAMS), run right after the timed region" % n_serial,
+                              "serialised_ms_per_frame": serial_ms / n_serial, "overlapped_schedule": overlapped}
         if dom_traffic is None and traffic_db.get(name):
             rf["traffic_note"] = "profiles traffic file was captured from other kernel sources (sha mismatch): not reported"
         out = {"config": desc, "n_gpus": H.world, "steps": steps, "warmup": warmup, "ms_per_frame": ms_per_step, "value": value, "unit": UNIT,
                "rays_per_frame": rays_all / steps, "slowest_rank_device_ms": slowest_rank_ms,
                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / n_e2e},
-               "gpu_launches": int(launches_all), "host_syncs_per_frame_rank0": syncs / steps, "waves_per_frame_rank0": waves / steps,
+               "gpu_launches": int(launches_all), "host_syncs_per_frame_rank0": syncs / steps, "waves_per_frame_rank0": waves / n_serial,
                "scene_build_ms": info.build_ms, "bvh_bytes": int(info.node_bytes + info.triangle_bytes), "texture_bytes": int(info.texture_bytes),
                "roofline": rf, "clocks": clk}
         if with_cpu and H.world == 1:

@@ -149,6 +149,9 @@ typedef struct RtxConfig {
                                          frame and is not traced; still counted in rays_shadow (the reference calls trace
                                          for it) and reported in rays_shadow_skipped.  Off by default: the bench traces
                                          every ray the reference traces.                                              */
+#define RTX_DEBUG_SERIAL_STREAMS  8u   /* measurement: shadow kernels on the frame's own stream instead of overlapping the next
+                                         wave, so that per-kernel CUDA-event times (RtxStats.closest_ms / shadow_ms) are
+                                         exclusive; the frame is a few percent slower                                     */
 #define RTX_DEBUG_ORDERED_SHADOW 2u   /* shadow rays: literal "closest hit of every item in bbox
                                          order" walk instead of the equivalent two-phase any-hit     */
 

@@ -119,6 +119,8 @@ struct RtxScene {
     DevBuf<float4> q_o, q_d; DevBuf<uint2> q_m;
     DevBuf<float4> s_o, s_d, s_c; DevBuf<uint32_t> s_r, s_slow;
     DevBuf<HitRec> hits; DevBuf<uint32_t> ctr_pool; DevBuf<uint32_t> overflow; DevBuf<Counters> counters;
+    cudaStream_t shadow_stream = nullptr; cudaEvent_t ev_shaded = nullptr, ev_shadow_done[2] = {nullptr, nullptr};   // shadow kernels overlap the next wave
+    uint32_t* h_pool = nullptr;             // pinned copy of the counter pool (per-wave exact / beyond counts are summed at the end of the frame)
     uint32_t* h_ctr = nullptr;              // pinned: 4 uint32 per-wave read-back + 8 * 66 level counters of a sync-free frame
     uint32_t wave_cap = 0;                  // rays one wave may hold (hit records, shadow queue / lights)
     uint32_t n_enabled_lights = 0;          // host mirror (rtx_scene_create / rtx_scene_set_lights)
@@ -377,7 +379,15 @@ int ensure_queues(RtxScene& sc, uint32_t max_recursion, uint32_t n_lights_enable
     const size_t qn = (size_t)levels * sc.level_cap;
     int rc;
     if ((rc = sc.q_o.alloc(qn)) || (rc = sc.q_d.alloc(qn)) || (rc = sc.q_m.alloc(qn))) return rc;
-    if ((rc = sc.s_o.alloc(sc.shadow_cap)) || (rc = sc.s_d.alloc(sc.shadow_cap)) || (rc = sc.s_c.alloc(sc.shadow_cap)) || (rc = sc.s_r.alloc(sc.shadow_cap)) || (rc = sc.s_slow.alloc(sc.shadow_cap))) return rc;
+    // the shadow queue is double-buffered: wave k+1's shade kernel fills one half while wave k's shadow kernels still drain the other
+    const size_t sq = 2 * (size_t)sc.shadow_cap;
+    if ((rc = sc.s_o.alloc(sq)) || (rc = sc.s_d.alloc(sq)) || (rc = sc.s_c.alloc(sq)) || (rc = sc.s_r.alloc(sq)) || (rc = sc.s_slow.alloc(sc.shadow_cap))) return rc;
+    if (!sc.shadow_stream) {
+        CU(cudaStreamCreateWithFlags(&sc.shadow_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&sc.ev_shaded, cudaEventDisableTiming));
+        for (int k = 0; k < 2; k++) CU(cudaEventCreateWithFlags(&sc.ev_shadow_done[k], cudaEventDisableTiming));
+        CU(cudaMallocHost(&sc.h_pool, (size_t)kCtrPool * 4));
+    }
     if (sc.group_root != 0xFFFFFFFFu && (rc = sc.s_beyond.alloc(sc.shadow_cap))) return rc;
     if ((rc = sc.hits.alloc(sc.wave_cap)) || (rc = sc.ctr_pool.alloc(kCtrPool)) || (rc = sc.overflow.alloc(4)) || (rc = sc.counters.alloc(1))) return rc;
     if (!sc.h_ctr) CU(cudaMallocHost(&sc.h_ctr, (4 + 8 * 66 + 8) * sizeof(uint32_t)));   // [0..3] overflow flags | [4..531] level counters | [532..539] one wave
@@ -633,8 +643,12 @@ int rtx_scene_create_ex(const RtxSceneDesc* d, int device, uint32_t scene_flags,
             const RtxItem& s = d->items[i];
             if (s.shape == RTX_SHAPE_MESH && is_identity16(s.trans) && is_identity16(s.tran_inverse)) { cand.push_back(i); gt += d->meshes[s.mesh].n_faces; }
         }
-        uint64_t max_tris = 4000000; if (const char* e = getenv("RTX_GROUP_MAX_TRIS")) max_tris = (uint64_t)atoll(e);
-        if (cand.size() >= 2 && gt <= max_tris && !getenv("RTX_NO_GROUP")) {
+        // not for a handful of quads (room walls: entering them directly costs less than a BLAS node plus the per-hit item work:
+        // room of spheres 762 ms ungrouped, 862 ms grouped), not for soups so large that a single-threaded build would dominate
+        uint64_t max_tris = 4000000, min_tris = 4096;
+        if (const char* e = getenv("RTX_GROUP_MAX_TRIS")) max_tris = (uint64_t)atoll(e);
+        if (const char* e = getenv("RTX_GROUP_MIN_TRIS")) min_tris = (uint64_t)atoll(e);
+        if (cand.size() >= 2 && gt >= min_tris && gt <= max_tris && !getenv("RTX_NO_GROUP")) {
             std::vector<Aabb3> boxes((size_t)gt); std::vector<uint32_t> p_item((size_t)gt), p_face((size_t)gt);
             size_t k = 0;
             for (uint32_t i : cand) {
@@ -748,6 +762,7 @@ int rtx_scene_destroy(RtxScene* sc) {
         P.hits.release(); P.out.release(); P.len.release(); P.recv.release(); P.res.release(); P.beyond.release();
         if (P.st) cudaStreamDestroy(P.st);
     }
+    if (sc->shadow_stream) { cudaStreamDestroy(sc->shadow_stream); cudaEventDestroy(sc->ev_shaded); cudaEventDestroy(sc->ev_shadow_done[0]); cudaEventDestroy(sc->ev_shadow_done[1]); cudaFreeHost(sc->h_pool); }
     if (sc->own_stream) cudaStreamDestroy(sc->own_stream);
     if (sc->fence) cudaEventDestroy(sc->fence);
     sc->nodes.release(); sc->tris.release(); sc->items.release(); sc->tlas_prims.release(); sc->fast_prims.release(); sc->s_beyond.release();
@@ -855,6 +870,7 @@ struct FrameCtx {
     RtxScene* sc; cudaStream_t st; FrameDev F; PixelList* pl; const RtxConfig* cfg; const RtxCamera* cam;
     void *d_rgba, *d_normals, *d_depth, *d_ids;
     bool want_stats, ordered, primary_single = false; uint32_t L; int gs;
+    cudaStream_t sst = nullptr; int shadow_buf = 0; bool shadow_pending[2] = {false, false};   // shadow stream, queue half of the next wave
     uint64_t launches = 0, rays_closest = 0, rays_shadow = 0, rays_exact = 0, rays_beyond = 0, primary = 0; uint32_t waves = 0, batches = 0; size_t ev_next = 2;
     cudaEvent_t event(size_t i) {
         while (sc->events.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); sc->events.push_back(e); }
@@ -867,7 +883,14 @@ struct FrameCtx {
 int launch_wave(FrameCtx& X, uint32_t d, uint32_t q_base, uint32_t n, const uint32_t* n_ptr, uint32_t* ctr, uint32_t child_off) {
     RtxScene* sc = X.sc; cudaStream_t st = X.st;
     RayQ Q = level_queue(*sc, d);
-    ShadowQ SQ{sc->s_o.p, sc->s_d.p, sc->s_c.p, sc->s_r.p, nullptr, sc->s_beyond.p};
+    // Shadow kernels run on their own stream: wave k's any-hit / beyond / exact kernels overlap wave k+1's closest-hit and shade
+    // kernels (they only add to the accumulators), which fills the tails of the persistent kernels — what a strong-scaled shard with
+    // its thin waves needs most.  The queue half a shade kernel writes must have been drained by the shadow kernels of two waves ago.
+    const int buf = X.shadow_buf; X.shadow_buf ^= 1;
+    const size_t so_off = (size_t)buf * sc->shadow_cap;
+    ShadowQ SQ{sc->s_o.p + so_off, sc->s_d.p + so_off, sc->s_c.p + so_off, sc->s_r.p + so_off, nullptr, sc->s_beyond.p};
+    cudaStream_t sst = X.sst;
+    if (X.shadow_pending[buf] && sst != st) CU(cudaStreamWaitEvent(st, sc->ev_shadow_done[buf], 0));
     cudaEvent_t e0 = X.event(X.ev_next), e1 = X.event(X.ev_next + 1), e2 = X.event(X.ev_next + 2), e3 = X.event(X.ev_next + 3);
     X.ev_next += 4;
     const bool verify = !n_ptr && getenv("RTX_VERIFY");
@@ -913,26 +936,28 @@ int launch_wave(FrameCtx& X, uint32_t d, uint32_t q_base, uint32_t n, const uint
         shade_kernel<<<blocks, kShadeBlock, 0, st>>>(sc->dev, X.F, Q, q_base, n, n_ptr, sc->hits.p, so);
         X.launches++;
     }
-    CU(cudaEventRecord(e2, st));
+    if (sst != st) { CU(cudaEventRecord(sc->ev_shaded, st)); CU(cudaStreamWaitEvent(sst, sc->ev_shaded, 0)); }
+    CU(cudaEventRecord(e2, sst));
     if (sc->n_enabled_lights > 0) {
         const int eb = sc->sm_count * 8;
         if (X.ordered) {
-            shadow_exact_kernel<false, true><<<eb, kTraceBlock, 0, st>>>(sc->dev, X.F, SQ, nullptr, ctr + 3, sc->shadow_cap, d, sc->counters.p);
+            shadow_exact_kernel<false, true><<<eb, kTraceBlock, 0, sst>>>(sc->dev, X.F, SQ, nullptr, ctr + 3, sc->shadow_cap, d, sc->counters.p);
             X.launches++;
         } else {
-            if (X.want_stats) shadow_any_kernel<true><<<sc->blocks_shadow_st, kTraceBlock, 0, st>>>(sc->dev, X.F, SQ, ctr + 3, sc->shadow_cap, d, ctr + 1, sc->s_slow.p, ctr + 4, sc->counters.p);
-            else shadow_any_kernel<false><<<sc->blocks_shadow, kTraceBlock, 0, st>>>(sc->dev, X.F, SQ, ctr + 3, sc->shadow_cap, d, ctr + 1, sc->s_slow.p, ctr + 4, sc->counters.p);
+            if (X.want_stats) shadow_any_kernel<true><<<sc->blocks_shadow_st, kTraceBlock, 0, sst>>>(sc->dev, X.F, SQ, ctr + 3, sc->shadow_cap, d, ctr + 1, sc->s_slow.p, ctr + 4, sc->counters.p);
+            else shadow_any_kernel<false><<<sc->blocks_shadow, kTraceBlock, 0, sst>>>(sc->dev, X.F, SQ, ctr + 3, sc->shadow_cap, d, ctr + 1, sc->s_slow.p, ctr + 4, sc->counters.p);
             if (sc->dev.group_root != 0xFFFFFFFFu) {
-                if (X.want_stats) shadow_beyond_kernel<true><<<eb, kTraceBlock, 0, st>>>(sc->dev, X.F, SQ, ctr + 5, sc->shadow_cap, d, sc->s_slow.p, ctr + 4, sc->counters.p);
-                else shadow_beyond_kernel<false><<<eb, kTraceBlock, 0, st>>>(sc->dev, X.F, SQ, ctr + 5, sc->shadow_cap, d, sc->s_slow.p, ctr + 4, sc->counters.p);
+                if (X.want_stats) shadow_beyond_kernel<true><<<eb, kTraceBlock, 0, sst>>>(sc->dev, X.F, SQ, ctr + 5, sc->shadow_cap, d, sc->s_slow.p, ctr + 4, sc->counters.p);
+                else shadow_beyond_kernel<false><<<eb, kTraceBlock, 0, sst>>>(sc->dev, X.F, SQ, ctr + 5, sc->shadow_cap, d, sc->s_slow.p, ctr + 4, sc->counters.p);
                 X.launches++;
             }
-            if (X.want_stats) shadow_exact_kernel<true, false><<<eb, kTraceBlock, 0, st>>>(sc->dev, X.F, SQ, sc->s_slow.p, ctr + 4, sc->shadow_cap, d, sc->counters.p);
-            else shadow_exact_kernel<false, false><<<eb, kTraceBlock, 0, st>>>(sc->dev, X.F, SQ, sc->s_slow.p, ctr + 4, sc->shadow_cap, d, sc->counters.p);
+            if (X.want_stats) shadow_exact_kernel<true, false><<<eb, kTraceBlock, 0, sst>>>(sc->dev, X.F, SQ, sc->s_slow.p, ctr + 4, sc->shadow_cap, d, sc->counters.p);
+            else shadow_exact_kernel<false, false><<<eb, kTraceBlock, 0, sst>>>(sc->dev, X.F, SQ, sc->s_slow.p, ctr + 4, sc->shadow_cap, d, sc->counters.p);
             X.launches += 2;
         }
     }
-    CU(cudaEventRecord(e3, st));
+    CU(cudaEventRecord(e3, sst));
+    if (sst != st) { CU(cudaEventRecord(sc->ev_shadow_done[buf], sst)); X.shadow_pending[buf] = true; }
     return RTX_OK;
 }
 
@@ -974,10 +999,18 @@ int render_frame_single(RtxScene* sc, const RtxCamera* cam, const RtxConfig* cfg
     const uint32_t chunk = sc->chunk;
     bool sync_free = n_primary <= chunk && !sc->no_sync_free && !getenv("RTX_FORCE_SYNC") && !getenv("RTX_VERIFY");
     uint32_t ovf[4] = {0, 0, 0, 0};
+    X.sst = (getenv("RTX_NO_OVERLAP") || getenv("RTX_VERIFY") || (cfg->debug_flags & RTX_DEBUG_SERIAL_STREAMS)) ? st : sc->shadow_stream;
+    struct ShadowStreamGuard { cudaStream_t s; ~ShadowStreamGuard() { cudaStreamSynchronize(s); } } sguard{sc->shadow_stream};   // no exit leaves it running
+    // everything the shadow stream did must be in the accumulators before they are resolved (or cleared again)
+    auto join_shadow = [&]() -> int {
+        for (int k = 0; k < 2; k++) if (X.shadow_pending[k]) { CU(cudaStreamWaitEvent(st, sc->ev_shadow_done[k], 0)); X.shadow_pending[k] = false; }
+        return RTX_OK;
+    };
 
     for (int attempt = 0; attempt < 2; attempt++) {
         X.launches = 0; X.rays_closest = X.rays_shadow = X.rays_exact = X.rays_beyond = X.primary = 0; X.waves = X.batches = 0; X.ev_next = 2;
-        X.primary_single = sync_free;
+        X.primary_single = sync_free; X.shadow_buf = 0;
+        if ((rc = join_shadow())) return rc;
         // events: [0] frame start, [1] frame end, then 4 per wave (closest start/end, shadow start/end)
         CU(cudaEventRecord(X.event(0), st));
         CU(cudaMemsetAsync(sc->ctr_pool.p, 0, kCtrPool * 4, st));
@@ -997,6 +1030,7 @@ int render_frame_single(RtxScene* sc, const RtxCamera* cam, const RtxConfig* cfg
                 if ((rc = launch_wave(X, d, 0, d == 1 ? n1 : sc->wave_cap, d == 1 ? nullptr : ctr - 8 + 2, ctr, 0))) return rc;
                 X.waves++;
             }
+            if ((rc = join_shadow())) return rc;
             resolve_kernel<<<std::min<uint32_t>((pl->n + 255) / 256, gs), 256, 0, st>>>(F, pl->d.p, pl->n, (uchar4*)d_rgba, (float*)d_normals, (float*)d_depth,
                                                                                     (uint32_t*)d_object_ids);
             X.launches++;
@@ -1037,9 +1071,18 @@ int render_frame_single(RtxScene* sc, const RtxCamera* cam, const RtxConfig* cfg
         uint32_t cur_p0 = 0, cur_s0 = 0;
         bool primary_left = pl->n > 0;
         uint32_t ctr_idx = 0;
+        // per-wave counts that only the shadow kernels know (rays re-walked exactly / checked behind the light) are summed from the
+        // counter pool once the shadow stream has been joined
+        auto harvest = [&](uint32_t used) -> int {
+            if (used) CU(cudaMemcpyAsync(sc->h_pool, sc->ctr_pool.p, (size_t)used * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            for (uint32_t k = 0; k + 8 <= used; k += 8) { X.rays_exact += sc->h_pool[k + 4]; X.rays_beyond += sc->h_pool[k + 5]; }
+            return RTX_OK;
+        };
         for (;;) {
             if (sc->cancel.load(std::memory_order_relaxed)) { CU(cudaStreamSynchronize(st)); return fail(RTX_E_CANCELLED, "frame cancelled by rtx_render_stop"); }
             if (sc->snap_req.load(std::memory_order_relaxed)) {
+                if ((rc = join_shadow())) return rc;
                 // progressive preview (the stream is idle here): pixels whose samples were all issued are normalised by the sample
                 // count, the pixel range in progress by the samples issued so far, the rest is cleared; rays still queued at
                 // deeper levels are simply not in the sums yet
@@ -1086,26 +1129,30 @@ int render_frame_single(RtxScene* sc, const RtxCamera* cam, const RtxConfig* cfg
             const uint32_t n = std::min(counts[d], chunk);
             const uint32_t q_base = counts[d] - n;
             counts[d] -= n;
-            if (ctr_idx + 8 > kCtrPool) {                                    // stream is idle here (we sync every wave)
+            if (ctr_idx + 8 > kCtrPool) {                                    // counter pool used up (16 Ki waves): harvest it and start over
+                if ((rc = join_shadow()) || (rc = harvest(ctr_idx))) return rc;
                 CU(cudaMemsetAsync(sc->ctr_pool.p, 0, kCtrPool * 4, st)); ctr_idx = 0;
             }
-            uint32_t* ctr = sc->ctr_pool.p + ctr_idx; ctr_idx += 8;          // [0] closest work, [1] shadow work, [2] child count, [3] shadow count, [4] slow count
+            uint32_t* ctr = sc->ctr_pool.p + ctr_idx; ctr_idx += 8;          // [0] closest work, [1] shadow work, [2] child count, [3] shadow count, [4] slow count, [5] beyond count
             if ((rc = launch_wave(X, d, q_base, n, nullptr, ctr, d + 1 <= L ? counts[d + 1] : 0))) return rc;
-            CU(cudaMemcpyAsync(sc->h_ctr + 532, ctr, 32, cudaMemcpyDeviceToHost, st));
+            // the host only needs what the SHADE kernel counted (children, shadow rays) to schedule the next wave; the shadow kernels
+            // of this wave keep running on their own stream while the next wave's closest-hit kernel starts
+            CU(cudaMemcpyAsync(sc->h_ctr + 532, ctr, 16, cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
             memcpy(sc->h_ctr, sc->h_ctr + 532, 16);
             if (d + 1 <= L) counts[d + 1] += sc->h_ctr[2];
-            X.rays_closest += n; X.rays_shadow += sc->h_ctr[3]; X.rays_exact += sc->h_ctr[536]; X.rays_beyond += sc->h_ctr[537];
+            X.rays_closest += n; X.rays_shadow += sc->h_ctr[3];
             X.waves++;
             if (d + 1 <= L && counts[d + 1] > sc->level_cap) return fail(RTX_E_INVALID, "internal: ray queue overflow");
             if (sc->h_ctr[3] > sc->shadow_cap) return fail(RTX_E_INVALID, "internal: shadow queue overflow");
         }
+        if ((rc = join_shadow())) return rc;
         resolve_kernel<<<std::min<uint32_t>((pl->n + 255) / 256, gs), 256, 0, st>>>(F, pl->d.p, pl->n, (uchar4*)d_rgba, (float*)d_normals, (float*)d_depth,
                                                                                 (uint32_t*)d_object_ids);
         X.launches++;
         CU(cudaEventRecord(X.event(1), st));
         CU(cudaMemcpyAsync(sc->h_ctr, sc->overflow.p, 16, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
+        if ((rc = harvest(ctr_idx))) return rc;                               // (synchronises st)
         CU(cudaGetLastError());
         memcpy(ovf, sc->h_ctr, 16);
         if (ovf[0]) return fail(RTX_E_INVALID, "internal: ray queue overflow");
