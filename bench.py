@@ -361,7 +361,8 @@ def measure_workload(H, name, steps, warmup, with_cpu, peak, peak_src, l2_gbs, t
         dom_traffic = None
         t = traffic_db.get(name)
         if t and traffic_db.get("source_sha") == source_sha():
-            dom_traffic = t
+            dom_k = "closest_kernel" if closest_ms >= shadow_ms else "shadow_any_kernel"
+            dom_traffic = t.get("kernels", {}).get(dom_k)
         rf = roofline_block(st0, closest_ms, shadow_ms, serial_ms, n_serial, waves, rays / steps, peak, peak_src, l2_gbs,
                             clk["sm_mhz"] if clk else None, prop.multi_processor_count, info.node_bytes + info.triangle_bytes,
                             (dom_traffic or {}).get("dram_bytes_per_launch"))
