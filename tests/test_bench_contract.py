@@ -34,13 +34,20 @@ def test_reference_arm_other_ranks_stay_silent():
 
 
 def test_committed_gpu_line_has_the_contract_keys():
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_v*_bench.json")))
-    assert files
-    d = json.load(open(files[-1]))
-    assert BASE_KEYS | {"clocks", "roofline", "cpu_baseline"} <= set(d)
-    assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["dtype"] == "f32" and d["gpu_launches"] > 0
+    d = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_n1.json")))
+    assert BASE_KEYS | {"clocks", "roofline", "cpu_baseline", "workloads"} <= set(d)
+    assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["dtype"] == "f32" and d["gpu_launches"] > 0 and d["scaling"] == "strong"
     rf = d["roofline"]
-    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(rf) and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-6
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic", "bounds"} <= set(rf) and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-6
+    b = rf["bounds"]                                                # north_star: the lesser of bytes/ray over bandwidth and flops/ray over the FP32 peak
+    assert b["binding"] in ("bandwidth", "fp32") and min(b["bound_bw_Grays_per_s"], b["bound_fp32_Grays_per_s"]) > 0 and b["l2_read_GBps_measured"] > 0
+    assert set(d["workloads"]) == {"c4_standin", "c3_standin", "c5"}
+    for w in d["workloads"].values():
+        assert w["value"] > 0 and w["ms_per_frame"] > 0 and {"roofline", "cpu_baseline", "e2e", "config"} <= set(w) and "workload" in w["config"]
+        assert "STAND-IN" in w["config"]["workload"] or "configs[4]" in w["config"]["workload"]
+    for n in (2, 4, 8):                                             # the same frame at every N
+        dn = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_n%d.json" % n)))
+        assert dn["n_gpus"] == n and dn["scaling"] == "strong" and dn["config"]["samples"] == d["config"]["samples"] and abs(dn["rays_per_step"] - d["rays_per_step"]) < 1e-6 * d["rays_per_step"]
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] == 1280 * 720 * 24 + d["e2e"]["d2h_bytes_per_step"] % (1280 * 720 * 24)
     assert d["e2e"]["value"] <= d["value"] * 1.001                  # host copies are inside the timed region
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
