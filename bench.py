@@ -280,8 +280,29 @@ def measure_workload(H, name, steps, warmup, with_cpu, peak, peak_src, l2_gbs, t
     info = rm.bvh_info()
     shard = abi.RtxShard(H.rank, H.world, 8, 4)
     pf = PeerFrame(rm._lib, w, h, H.rank, H.world, H.local)
-    ptrs = pf.pointers()
     stream = torch.cuda.current_stream(H.dev).cuda_stream
+    sr = None
+    if pf.ok and os.environ.get("RTX_BENCH_NO_IPC") == "1":            # exercise the fallback on a box that does have peer memory
+        pf.close(); pf.ok = False
+    if pf.ok:
+        ptrs = pf.pointers()
+        gather_mode = "resolve kernels store into rank 0's frame buffers over NVLink peer memory (CUDA IPC)"
+    else:
+        # no peer memory between these GPUs: every rank resolves locally, ONE NCCL gather of the packed shards, one scatter kernel
+        from rustray_b200.distributed import ShardedRenderer
+
+        class _NcclFrame:
+            def __init__(self, s): self.s = s
+            def finish(self): self.s.gather()
+            def download(self, frame, stream_ptr=0):
+                torch.cuda.synchronize()
+                for src, dst in zip((self.s.rgba, self.s.normals, self.s.depth, self.s.ids), (frame.image, frame.normals, frame.depth, frame.objects)):
+                    dst.reshape(-1)[:] = src.cpu().numpy().view(dst.dtype).reshape(-1)
+            def close(self): pass
+        sr = ShardedRenderer(rm, w, h, H.rank, H.world, device=H.dev)
+        ptrs = [sr.rgba.data_ptr(), sr.normals.data_ptr(), sr.depth.data_ptr(), sr.ids.data_ptr()]
+        pf = _NcclFrame(sr)
+        gather_mode = "CUDA IPC unavailable: one NCCL gather of the packed G-buffer + one scatter kernel"
 
     def render(c):
         st = abi.RtxStats()
@@ -370,7 +391,7 @@ def measure_workload(H, name, steps, warmup, with_cpu, peak, peak_src, l2_gbs, t
                               "serialised_ms_per_frame": serial_ms / n_serial, "overlapped_schedule": overlapped}
         if dom_traffic is None and traffic_db.get(name):
             rf["traffic_note"] = "profiles traffic file was captured from other kernel sources (sha mismatch): not reported"
-        out = {"config": desc, "n_gpus": H.world, "steps": steps, "warmup": warmup, "ms_per_frame": ms_per_step, "value": value, "unit": UNIT,
+        out = {"config": desc, "n_gpus": H.world, "gather_mode": gather_mode, "steps": steps, "warmup": warmup, "ms_per_frame": ms_per_step, "value": value, "unit": UNIT,
                "rays_per_frame": rays_all / steps, "slowest_rank_device_ms": slowest_rank_ms,
                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / n_e2e},
                "gpu_launches": int(launches_all), "host_syncs_per_frame_rank0": syncs / steps, "waves_per_frame_rank0": waves / n_serial,
@@ -466,7 +487,7 @@ def run_ours(args):
                 "ms_per_step": main["ms_per_frame"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": workload_config(H.world), "clocks": main["clocks"],
                 "e2e": main["e2e"], "gpu_launches": main["gpu_launches"], "roofline": main["roofline"], "rays_per_step": main["rays_per_frame"],
-                "ms_per_frame": main["ms_per_frame"], "slowest_rank_device_ms": main["slowest_rank_device_ms"],
+                "ms_per_frame": main["ms_per_frame"], "slowest_rank_device_ms": main["slowest_rank_device_ms"], "gather_mode": main["gather_mode"],
                 "host_syncs_per_frame_rank0": main["host_syncs_per_frame_rank0"], "scene_build_ms": main["scene_build_ms"],
                 "opt_skip_zero_shadow": {"ms_per_frame": skip_ms, "rays_skipped_rank0": int(skip_st.rays_shadow_skipped),
                                          "note": "opt-in flag, image-identical; informational, not part of value/e2e"},

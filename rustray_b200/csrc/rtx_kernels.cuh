@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(kShadeBlock, RTX_SHADE_MIN_BLOCKS) shade_kerne
         float3 hit_point = f3(0, 0, 0), surface_normal = f3(0, 0, 1); float coef_d = 0.0f;
         float4 base_color = make_float4(0, 0, 0, 0), specular_color = make_float4(0, 0, 0, 0);
         float shininess = 0.0f, mat_alpha = 1.0f, shadow_z_lo = 1.0f; bool recv_shadow = false, mat_mc = false;
-        float3 direct = f3(0, 0, 0), constant = f3(0, 0, 0);
+        float3 direct = f3(0, 0, 0), constant = f3(0, 0, 0); float depth_add = 0.0f;
 
         // --- queue space: ONE reservation per warp for the shadow rays of all lights (and, before the light loop, one for both
         // child rays).  Every warp of the GPU hits the same two counters, so the atomics' round trips are long: they are issued as
@@ -467,8 +467,8 @@ __global__ void __launch_bounds__(kShadeBlock, RTX_SHADE_MIN_BLOCKS) shade_kerne
             uint32_t face_id;
             const float3 normal = hit_normal(S, item, o, d, h.t, h.prim, h.flags, face_id);
             const float hit_dist = h.t;
-            if (depth == 1) {                                                    // :400-403 depth / normal sums
-                atomicAdd(&F.accum_c[pixel], make_float4(0.0f, 0.0f, 0.0f, hit_dist));
+            if (depth == 1) {                                                    // :400-403 depth / normal sums (the depth rides along with the colour below)
+                depth_add = hit_dist;
                 atomicAdd(&F.accum_n[pixel], make_float4(normal.x, normal.y, normal.z, 0.0f));
             }
             if (rflags & RF_ID_OWNER) F.ids[pixel] = item.id;
@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(kShadeBlock, RTX_SHADE_MIN_BLOCKS) shade_kerne
         }
         if (hit) {
             const float3 acc = direct + constant;
-            if (acc.x != 0.0f || acc.y != 0.0f || acc.z != 0.0f) atomicAdd(&F.accum_c[pixel], make_float4(acc.x, acc.y, acc.z, 0.0f));
+            if (acc.x != 0.0f || acc.y != 0.0f || acc.z != 0.0f || depth_add != 0.0f) atomicAdd(&F.accum_c[pixel], make_float4(acc.x, acc.y, acc.z, depth_add));
         }
         // --- child rays ---
         ch_base = __shfl_sync(0xffffffffu, ch_base, 0);

@@ -89,7 +89,9 @@ def gather_frame_cpu(rank: int, world: int, width: int, height: int, local_frame
 class PeerFrame:
     """Frame buffers on rank 0 that every rank renders into through NVLink peer memory (CUDA IPC handle broadcast once).
     `pointers()` are the d_rgba / d_normals / d_depth / d_object_ids to pass to RendererManager.render_device together
-    with this rank's shard; `finish()` is the barrier after which rank 0 holds the whole frame."""
+    with this rank's shard; `finish()` is the barrier after which rank 0 holds the whole frame.  `ok` is False on EVERY rank when
+    any rank could not create / open the buffers (no peer access between the GPUs): the caller then gathers with NCCL
+    (ShardedRenderer)."""
 
     def __init__(self, lib, width: int, height: int, rank: int, world: int, device_index: int, group=None):
         import ctypes as C
@@ -97,17 +99,31 @@ class PeerFrame:
         import torch.distributed as dist
         self.lib, self.w, self.h, self.rank, self.world, self.group = lib, width, height, rank, world, group
         self._g = C.c_void_p()
+        self.ptrs = [0, 0, 0, 0]
         handle = (C.c_uint8 * 64)()
+        good = 1
         if rank == 0:
-            _check(lib, lib.rtx_gbuffer_create(device_index, width, height, C.byref(self._g)))
-            _check(lib, lib.rtx_gbuffer_export(self._g, handle))
+            if lib.rtx_gbuffer_create(device_index, width, height, C.byref(self._g)) != 0:
+                good = 0
+            elif world > 1 and lib.rtx_gbuffer_export(self._g, handle) != 0:
+                good = 0
         if world > 1:
-            t = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=torch.device("cuda", device_index))
+            dev = torch.device("cuda", device_index)
+            t = torch.tensor(list(bytes(handle)) + [good], dtype=torch.uint8, device=dev)
             dist.broadcast(t, src=0, group=group)
-            if rank != 0:
-                raw = bytes(t.cpu().tolist())
-                C.memmove(handle, raw, 64)
-                _check(lib, lib.rtx_gbuffer_open(device_index, width, height, handle, C.byref(self._g)))
+            raw = bytes(t.cpu().tolist())
+            good = raw[64]
+            if rank != 0 and good:
+                C.memmove(handle, raw[:64], 64)
+                if lib.rtx_gbuffer_open(device_index, width, height, handle, C.byref(self._g)) != 0:
+                    good = 0
+            f = torch.tensor([good], dtype=torch.int32, device=dev)
+            dist.all_reduce(f, op=dist.ReduceOp.MIN, group=group)
+            good = int(f.item())
+        self.ok = bool(good)
+        if not self.ok:
+            self.close()
+            return
         p = [C.c_void_p() for _ in range(4)]
         _check(lib, lib.rtx_gbuffer_pointers(self._g, *[C.byref(x) for x in p]))
         self.ptrs = [x.value for x in p]
@@ -130,6 +146,7 @@ class PeerFrame:
         if self._g:
             self.lib.rtx_gbuffer_destroy(self._g)
             self._g = None
+        self.ptrs = [0, 0, 0, 0]
 
 
 def _check(lib, rc: int) -> None:
