@@ -121,6 +121,7 @@ class PeerFrame:
             dist.all_reduce(f, op=dist.ReduceOp.MIN, group=group)
             good = int(f.item())
         self.ok = bool(good)
+        self._token = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", device_index)) if world > 1 else None
         if not self.ok:
             self.close()
             return
@@ -132,9 +133,12 @@ class PeerFrame:
         return self.ptrs
 
     def finish(self) -> None:
+        """End of the frame on the DEVICE timeline: a one-element all-reduce enqueued behind this rank's frame.  On rank 0 whatever is
+        enqueued next (the D2H copy of the frame, the timing event) runs after every rank's resolve kernel has finished — its peer
+        stores are complete at kernel end.  Unlike dist.barrier() the host does not block here."""
         import torch.distributed as dist
         if self.world > 1:
-            dist.barrier(group=self.group)
+            dist.all_reduce(self._token, group=self.group)
 
     def download(self, frame, stream_ptr=0) -> None:
         """rank 0: copy the assembled frame into a renderer.Frame (page-locked host buffers)."""
