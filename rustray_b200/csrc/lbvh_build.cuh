@@ -225,6 +225,18 @@ __global__ void collapse_kernel(const Task* __restrict__ tasks, uint32_t n_tasks
     out_nodes[task.wide] = w;
 }
 
+// Triangle records (a|face, b|0, c|0 — 48 B) in leaf order, straight from the mesh arrays already on the device.
+__global__ void pack_tris_kernel(const uint32_t* __restrict__ prim_order, uint32_t n, const float* __restrict__ verts, const uint32_t* __restrict__ idx,
+                                 float4* __restrict__ tris) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t f = prim_order[k];
+    const uint32_t ia = idx[3 * (size_t)f], ib = idx[3 * (size_t)f + 1], ic = idx[3 * (size_t)f + 2];
+    tris[3 * (size_t)k] = make_float4(verts[3 * (size_t)ia], verts[3 * (size_t)ia + 1], verts[3 * (size_t)ia + 2], __uint_as_float(f));
+    tris[3 * (size_t)k + 1] = make_float4(verts[3 * (size_t)ib], verts[3 * (size_t)ib + 1], verts[3 * (size_t)ib + 2], 0.f);
+    tris[3 * (size_t)k + 2] = make_float4(verts[3 * (size_t)ic], verts[3 * (size_t)ic + 1], verts[3 * (size_t)ic + 2], 0.f);
+}
+
 // Scratch memory of the builder, grown on demand and reused from mesh to mesh (a scene of 64 meshes would otherwise pay 64 x 17
 // cudaMalloc / cudaFree pairs, each a device synchronisation).
 struct Workspace {
@@ -256,7 +268,9 @@ struct Workspace {
 // Host driver.  d_boxes: n boxes on the current device.  Results are copied into `out` (host): the scene assembly of
 // rtx_scene_create (node / primitive index offsets, triangle packing) is shared with the host builder.
 // Returns cudaSuccess or the first CUDA error; *deep = 1 when the Morton tree does not fit `depth_limit` levels.
-inline cudaError_t build_on_device(Workspace& W, const Box* h_boxes, uint32_t n, WideBvh& out, int depth_limit, int* deep, float* device_ms) {
+// keep_order_on_device: the leaf order stays in W.prim_order (the caller packs the triangles with a kernel) and out.prim_order is left empty.
+inline cudaError_t build_on_device(Workspace& W, const Box* h_boxes, uint32_t n, WideBvh& out, int depth_limit, int* deep, float* device_ms,
+                                   bool keep_order_on_device = false) {
     out.nodes.clear(); out.prim_order.clear(); out.max_depth = 0;
     if (deep) *deep = 0;
     if (n == 0) return cudaSuccess;
@@ -301,9 +315,9 @@ inline cudaError_t build_on_device(Workspace& W, const Box* h_boxes, uint32_t n,
     if (h[4] || h[1] != n) { e = cudaErrorUnknown; goto done; }
     out.max_depth = (int)h[3];
     if (depth_limit > 0 && out.max_depth > depth_limit) { if (deep) *deep = 1; goto done; }
-    out.nodes.resize(h[0]); out.prim_order.resize(n);
+    out.nodes.resize(h[0]);
     LB(cudaMemcpy(out.nodes.data(), W.nodes, (size_t)h[0] * sizeof(WideNode), cudaMemcpyDeviceToHost));
-    LB(cudaMemcpy(out.prim_order.data(), W.prim_order, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    if (!keep_order_on_device) { out.prim_order.resize(n); LB(cudaMemcpy(out.prim_order.data(), W.prim_order, (size_t)n * 4, cudaMemcpyDeviceToHost)); }
     if (device_ms) cudaEventElapsedTime(device_ms, e0, e1);
 done:
 #undef LB

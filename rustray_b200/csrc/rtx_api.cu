@@ -453,10 +453,10 @@ int rtx_scene_create_ex(const RtxSceneDesc* d, int device, uint32_t scene_flags,
     // Morton-order wide BVH built by kernels (lbvh_build.cuh); a tree too deep for the traversal stack falls back to the host builder
     lbvh::Workspace lbvh_ws;
     struct WsGuard { lbvh::Workspace& w; ~WsGuard() { w.release(); } } ws_guard{lbvh_ws};
-    auto build_boxes_on_device = [&](const std::vector<Aabb3>& boxes, WideBvh& bvh) -> bool {
+    auto build_boxes_on_device = [&](const std::vector<Aabb3>& boxes, WideBvh& bvh, bool keep_order = false) -> bool {
         int deep = 0; float ms = 0.f;
         static_assert(sizeof(lbvh::Box) == sizeof(Aabb3), "box layout");
-        const cudaError_t e = lbvh::build_on_device(lbvh_ws, reinterpret_cast<const lbvh::Box*>(boxes.data()), (uint32_t)boxes.size(), bvh, kBlasDepthLimit, &deep, &ms);
+        const cudaError_t e = lbvh::build_on_device(lbvh_ws, reinterpret_cast<const lbvh::Box*>(boxes.data()), (uint32_t)boxes.size(), bvh, kBlasDepthLimit, &deep, &ms, keep_order);
         if (e != cudaSuccess) cudaGetLastError();
         if (e == cudaSuccess && !deep) sc->device_build_ms += ms;
         return e == cudaSuccess && !deep;
@@ -516,6 +516,7 @@ int rtx_scene_create_ex(const RtxSceneDesc* d, int device, uint32_t scene_flags,
         }
         if (cudaGetLastError() != cudaSuccess) return bail(RTX_E_CUDA, "mesh array upload failed");
     }
+    bool tris_on_device = false;                                          // RTX_SCENE_DEVICE_BVH: sc->tris is filled by kernels, h_tris stays empty
     std::atomic<int> bad_index{0};                                        // 1 vertex, 2 uv, 3 normal index out of range (checked by the worker threads below)
     phase("mesh arrays uploaded");
     // BLAS builds are independent: one host thread per mesh, up to the hardware concurrency (config 5: 64 meshes of 156 k triangles).
@@ -564,24 +565,55 @@ int rtx_scene_create_ex(const RtxSceneDesc* d, int device, uint32_t scene_flags,
             for (uint32_t mi = 0; mi < d->n_meshes; mi++) max_faces = std::max(max_faces, d->meshes[mi].n_faces);
             lbvh_ws.reserve(max_faces);                                   // one allocation for the largest mesh, reused by all
         }
-        if (device_bvh)
+        if (device_bvh) {
+            // the triangle array is laid out up front (mesh after mesh, then room for a merged BLAS) and every mesh's records are
+            // packed by a kernel from the mesh arrays already on the device: no host packing, no 48 B/triangle upload
+            uint64_t total = 0, group_room = 0;
+            for (uint32_t mi = 0; mi < d->n_meshes; mi++) total += d->meshes[mi].n_faces;
+            for (uint32_t i = 0; i < d->n_items; i++)
+                if (d->items[i].shape == RTX_SHAPE_MESH && is_identity16(d->items[i].trans) && is_identity16(d->items[i].tran_inverse)) group_room += d->meshes[d->items[i].mesh].n_faces;
+            if (group_room > 4000000) group_room = 0;
+            int rc0 = sc->tris.alloc((size_t)(total + group_room) * 3);
+            if (rc0) { std::string keep = g_err; rtx_scene_destroy(sc); g_err = keep; return rc0; }
+            tris_on_device = true;
+            uint64_t toff = 0;
             for (uint32_t mi = 0; mi < d->n_meshes; mi++) {
-                if (!build_boxes_on_device(mesh_boxes[mi], bvhs[mi])) build_wide_bvh(mesh_boxes[mi].data(), d->meshes[mi].n_faces, bvhs[mi], kBlasDepthLimit);
+                const RtxMesh& m = d->meshes[mi]; const MeshOff& o = moff[mi];
+                if (build_boxes_on_device(mesh_boxes[mi], bvhs[mi], true)) {
+                    lbvh::pack_tris_kernel<<<(m.n_faces + 255) / 256, 256>>>(lbvh_ws.prim_order, m.n_faces, sc->verts.p + o.vert, sc->idx.p + o.idx, sc->tris.p + toff * 3);
+                } else {                                                  // Morton tree too deep for the stack: host builder, host packing, one copy
+                    build_wide_bvh(mesh_boxes[mi].data(), m.n_faces, bvhs[mi], kBlasDepthLimit);
+                    std::vector<float4> t((size_t)m.n_faces * 3);
+                    for (size_t k = 0; k < bvhs[mi].prim_order.size(); k++) {
+                        const uint32_t f = bvhs[mi].prim_order[k];
+                        const float* a = m.vertices + 3 * (size_t)m.indices[3 * (size_t)f];
+                        const float* b = m.vertices + 3 * (size_t)m.indices[3 * (size_t)f + 1];
+                        const float* c = m.vertices + 3 * (size_t)m.indices[3 * (size_t)f + 2];
+                        float fb; memcpy(&fb, &f, 4);
+                        t[3 * k] = make_float4(a[0], a[1], a[2], fb); t[3 * k + 1] = make_float4(b[0], b[1], b[2], 0.f); t[3 * k + 2] = make_float4(c[0], c[1], c[2], 0.f);
+                    }
+                    cudaMemcpy(sc->tris.p + toff * 3, t.data(), t.size() * sizeof(float4), cudaMemcpyHostToDevice);
+                }
+                toff += m.n_faces;
                 std::vector<Aabb3>().swap(mesh_boxes[mi]);
             }
+            if (cudaGetLastError() != cudaSuccess) return bail(RTX_E_CUDA, "triangle packing failed");
+        }
     }
     if (device_bvh) phase("device BLAS builds");
+    uint32_t n_mesh_tris = 0;
     {
         // node / triangle offsets per mesh, then the meshes are packed side by side by a pool of threads (30 M float4 for config 5)
         std::vector<uint32_t> node_off(d->n_meshes + 1, 0), tri_off(d->n_meshes + 1, 0);
         for (uint32_t mi = 0; mi < d->n_meshes; mi++) {
             const WideBvh& bvh = bvhs[mi];
             if (bvh.max_depth >= kStack - 2 || 2 * bvh.max_depth + 2 * 6 + 4 > kLaneStack) return bail(RTX_E_INVALID, "BLAS too deep for the traversal stack");
-            node_off[mi + 1] = node_off[mi] + (uint32_t)bvh.nodes.size(); tri_off[mi + 1] = tri_off[mi] + (uint32_t)bvh.prim_order.size();
+            node_off[mi + 1] = node_off[mi] + (uint32_t)bvh.nodes.size(); tri_off[mi + 1] = tri_off[mi] + d->meshes[mi].n_faces;
             sc->mesh_root[mi] = node_off[mi]; sc->mesh_tri_base[mi] = tri_off[mi];
         }
         h_nodes.reserve(((size_t)node_off[d->n_meshes] + 2 * (size_t)d->n_items + 64) * 5);    // room for the TLASes (a merged BLAS may still reallocate)
-        h_nodes.resize((size_t)node_off[d->n_meshes] * 5); h_tris.resize((size_t)tri_off[d->n_meshes] * 3);
+        h_nodes.resize((size_t)node_off[d->n_meshes] * 5); if (!tris_on_device) h_tris.resize((size_t)tri_off[d->n_meshes] * 3);
+        n_mesh_tris = tri_off[d->n_meshes];
         std::atomic<uint32_t> next{0};
         auto pack = [&]() {
             for (uint32_t mi = next.fetch_add(1); mi < d->n_meshes; mi = next.fetch_add(1)) {
@@ -592,8 +624,8 @@ int rtx_scene_create_ex(const RtxSceneDesc* d, int device, uint32_t scene_flags,
                     n.child_base += node_off[mi]; n.prim_base += tri_off[mi];
                     memcpy(np + 5 * k, &n, 80);
                 }
-                float4* tp = h_tris.data() + (size_t)tri_off[mi] * 3;
-                for (size_t k = 0; k < bvh.prim_order.size(); k++) {
+                float4* tp = tris_on_device ? nullptr : h_tris.data() + (size_t)tri_off[mi] * 3;
+                for (size_t k = 0; !tris_on_device && k < bvh.prim_order.size(); k++) {
                     const uint32_t f = bvh.prim_order[k];
                     const float* a = m.vertices + 3 * (size_t)m.indices[3 * (size_t)f];
                     const float* b = m.vertices + 3 * (size_t)m.indices[3 * (size_t)f + 1];
@@ -612,7 +644,7 @@ int rtx_scene_create_ex(const RtxSceneDesc* d, int device, uint32_t scene_flags,
         if (d->n_meshes) pack();
         for (std::thread& t : pool) t.join();
     }
-    sc->n_blas_nodes = (uint32_t)(h_nodes.size() / 5); sc->n_tris = (uint32_t)(h_tris.size() / 3);
+    sc->n_blas_nodes = (uint32_t)(h_nodes.size() / 5); sc->n_tris = n_mesh_tris;
     phase("BLAS nodes + triangles assembled");
 
     // ---- items ----
@@ -666,21 +698,28 @@ int rtx_scene_create_ex(const RtxSceneDesc* d, int device, uint32_t scene_flags,
             WideBvh bvh;
             if (!device_bvh || !build_boxes_on_device(boxes, bvh)) build_wide_bvh(boxes.data(), (uint32_t)gt, bvh, kBlasDepthLimit);
             if (!(bvh.max_depth >= kStack - 2 || 2 * bvh.max_depth + 2 * 6 + 4 > kLaneStack)) {       // too deep: keep the per-item structure only
-                const uint32_t node_off = (uint32_t)(h_nodes.size() / 5), tri_off = (uint32_t)(h_tris.size() / 3);
+                const uint32_t node_off = (uint32_t)(h_nodes.size() / 5), tri_off = sc->n_tris;
                 append_nodes(h_nodes, bvh, node_off, tri_off);
+                std::vector<float4> g_tris;                                  // device mode: copied behind the per-mesh records
+                std::vector<float4>& gt_out = tris_on_device ? g_tris : h_tris;
+                gt_out.reserve(gt_out.size() + (size_t)gt * 3);
                 for (uint32_t pi : bvh.prim_order) {
                     const RtxMesh& m = d->meshes[d->items[p_item[pi]].mesh]; const uint32_t f = p_face[pi];
                     const float* a = m.vertices + 3 * (size_t)m.indices[3 * (size_t)f];
                     const float* b = m.vertices + 3 * (size_t)m.indices[3 * (size_t)f + 1];
                     const float* c = m.vertices + 3 * (size_t)m.indices[3 * (size_t)f + 2];
                     float fb, ib; memcpy(&fb, &f, 4); memcpy(&ib, &p_item[pi], 4);
-                    h_tris.push_back(make_float4(a[0], a[1], a[2], fb));
-                    h_tris.push_back(make_float4(b[0], b[1], b[2], ib));            // .w = item: what the reference does per item happens per accepted triangle
-                    h_tris.push_back(make_float4(c[0], c[1], c[2], 0.f));
+                    gt_out.push_back(make_float4(a[0], a[1], a[2], fb));
+                    gt_out.push_back(make_float4(b[0], b[1], b[2], ib));            // .w = item: what the reference does per item happens per accepted triangle
+                    gt_out.push_back(make_float4(c[0], c[1], c[2], 0.f));
+                }
+                if (tris_on_device) {
+                    if ((size_t)(tri_off + gt) * 3 > sc->tris.n) return bail(RTX_E_INVALID, "internal: merged BLAS does not fit the triangle array");
+                    CU(cudaMemcpy(sc->tris.p + (size_t)tri_off * 3, g_tris.data(), g_tris.size() * sizeof(float4), cudaMemcpyHostToDevice));
                 }
                 sc->group_root = node_off; sc->group_items = cand; sc->n_group_tris = (uint32_t)gt;
                 for (uint32_t i : cand) sc->h_items[i].flags |= IF_GROUPED;
-                sc->n_blas_nodes = (uint32_t)(h_nodes.size() / 5); sc->n_tris = (uint32_t)(h_tris.size() / 3);
+                sc->n_blas_nodes = (uint32_t)(h_nodes.size() / 5); sc->n_tris = tri_off + (uint32_t)gt;
             }
         }
     }
@@ -731,7 +770,7 @@ int rtx_scene_create_ex(const RtxSceneDesc* d, int device, uint32_t scene_flags,
     phase("TLAS, materials, textures");
     // ---- upload ----
     int rc;
-    if ((rc = sc->nodes.upload(h_nodes)) || (rc = sc->tris.upload(h_tris)) || (rc = sc->items.upload(sc->h_items)) ||
+    if ((rc = sc->nodes.upload(h_nodes)) || (!tris_on_device && (rc = sc->tris.upload(h_tris))) || (rc = sc->items.upload(sc->h_items)) ||
         (rc = sc->tlas_prims.upload(tlas_prims)) || (rc = sc->fast_prims.upload(fast_prims)) ||
         (rc = sc->mats.upload(h_mats)) || (rc = sc->texs.upload(h_texs)) || (rc = sc->texels.upload(h_texels)) || (rc = sc->lights.upload(h_lights))) {
         std::string keep = g_err; rtx_scene_destroy(sc); g_err = keep; return rc;

@@ -203,6 +203,28 @@ def test_shards_union_equals_full_frame_and_pack_roundtrip():
         assert np.array_equal(out[3].cpu().numpy().astype(np.uint32).reshape(h, w), full.objects)
         assert np.array_equal(out[2].cpu().numpy().reshape(h, w), full.depth)
         assert rays == full.stats.rays_closest + full.stats.rays_shadow   # work is additive over shards
+        # ONE scatter kernel for the gathered buffer of all ranks (rank r's packed shard at r * stride), as rank 0 runs it after the NCCL gather
+        sizes = [int(lib.rtx_shard_packed_bytes(w, h, C.byref(abi.RtxShard(r, world, tile[0], tile[1])))) for r in range(world)]
+        stride = (max(sizes) + 15) // 16 * 16
+        allbuf = torch.zeros(stride * world, dtype=torch.uint8, device=dev)
+        for r in range(world):
+            sh = abi.RtxShard(r, world, tile[0], tile[1])
+            g.render_device(cam, cfg, sh, rgba, nrm, dep, ids)
+            assert lib.rtx_shard_pack(w, h, C.byref(sh), rgba.data_ptr(), nrm.data_ptr(), dep.data_ptr(), ids.data_ptr(), allbuf.data_ptr() + r * stride, None) == 0
+        out2 = [torch.full_like(rgba, 9), torch.full_like(nrm, 9), torch.full_like(dep, 9), torch.full_like(ids, 9)]
+        assert lib.rtx_shard_unpack_all(w, h, world, tile[0], tile[1], 0, allbuf.data_ptr(), stride, out2[0].data_ptr(), out2[1].data_ptr(), out2[2].data_ptr(),
+                                        out2[3].data_ptr(), None) == 0
+        torch.cuda.synchronize()
+        assert np.array_equal(out2[3].cpu().numpy().astype(np.uint32).reshape(h, w), full.objects) and np.array_equal(out2[2].cpu().numpy().reshape(h, w), full.depth)
+        assert lsb_stats(out2[0].cpu().numpy().reshape(h, w, 4), full.image)[0] >= 0.9999
+        # first_rank = 1 leaves rank 0's own pixels alone (they are already in place on rank 0)
+        out3 = [torch.full_like(rgba, 9), torch.full_like(nrm, 9), torch.full_like(dep, 9), torch.zeros_like(ids)]
+        assert lib.rtx_shard_unpack_all(w, h, world, tile[0], tile[1], 1, allbuf.data_ptr(), stride, out3[0].data_ptr(), out3[1].data_ptr(), out3[2].data_ptr(),
+                                        out3[3].data_ptr(), None) == 0
+        torch.cuda.synchronize()
+        mine = shard_pixels(w, h, 0, world, *tile)
+        got = out3[3].cpu().numpy().astype(np.uint32)
+        assert (got[mine] == 0).all() and np.array_equal(np.delete(got, mine), np.delete(full.objects.reshape(-1), mine))
 
 
 def test_update_items_and_lights_between_frames():
