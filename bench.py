@@ -64,9 +64,10 @@ def measured_peaks():
 
 
 def source_sha():
-    """Identity of the kernel sources: profiles/*_traffic.json is only trusted when it was captured from the same code."""
+    """Identity of the kernel sources (the frame's kernels, the device functions they inline and the host BVH builder that shapes
+    the trees they walk): profiles/*_traffic.json is only trusted when it was captured from the same code."""
     h = hashlib.sha256()
-    for f in ("rtx_api.cu", "rtx_kernels.cuh", "rtx_device.cuh", "bvh_build.cpp", "bvh_build.h"):
+    for f in ("rtx_kernels.cuh", "rtx_device.cuh", "bvh_build.cpp", "bvh_build.h"):
         h.update(open(os.path.join(ROOT, "rustray_b200", "csrc", f), "rb").read())
     return h.hexdigest()[:16]
 

@@ -853,7 +853,7 @@ int rtx_scene_update_items(RtxScene* sc, const RtxItemXform* x, size_t n) {
         for (uint32_t gi : sc->group_items) if (!is_identity16(sc->src_items[gi].trans) || !is_identity16(sc->src_items[gi].tran_inverse)) intact = false;
         if (!intact) {
             for (uint32_t gi : sc->group_items) sc->h_items[gi].flags &= ~IF_GROUPED;
-            sc->group_root = 0xFFFFFFFFu; sc->group_items.clear();
+            sc->group_root = 0xFFFFFFFFu; sc->group_items.clear(); sc->n_group_tris = 0;
             refresh_dev(*sc);
         }
     }

@@ -349,6 +349,40 @@ def test_one_process_two_gpus_equals_one_gpu():
         assert two.pick(cam, w // 2, h // 2) == one.pick(cam, w // 2, h // 2)
 
 
+@pytest.mark.skipif("_n_gpus() < 2")
+def test_one_process_two_gpus_with_a_merged_blas():
+    """The replicas of a multi-GPU handle carry the merged world-space BLAS and the fast TLAS too."""
+    sc = synthetic.atrium_scene(320, 180, detail=0.04, tex_size=32, samples=2, monte_carlo=True)
+    fs, cam, cfg = scene_to_abi(sc)
+    one, two = RendererManager(320, 180, fs, device=0), RendererManager(320, 180, fs, devices=[0, 1])
+    assert one.bvh_info().grouped_items > 100
+    a, b = one.start(cam, cfg), two.start(cam, cfg)
+    assert np.array_equal(a.objects, b.objects) and np.array_equal(a.depth, b.depth) and lsb_stats(a.image, b.image)[0] >= 0.9999
+    assert (a.stats.rays_closest, a.stats.rays_shadow) == (b.stats.rays_closest, b.stats.rays_shadow)
+
+
+def test_moving_an_item_of_the_merged_blas_dissolves_the_group():
+    """rtx_scene_update_items on a grouped item: world space is no longer its object space, the group is dissolved and the
+    frame must still be the reference's (Scene::apply_frame + update, scene.rs:1695-1713)."""
+    from rustray_b200.scene_loader import mat_inverse, mat_translation
+    sc = synthetic.atrium_scene(240, 135, detail=0.04, tex_size=32, samples=1, monte_carlo=False)
+    fs, cam, cfg = scene_to_abi(sc)
+    g, c = RendererManager(240, 135, fs), OracleRenderer(fs)
+    assert g.bvh_info().grouped_items > 100
+    names = fs.item_names
+    k = names.index("plant2")
+    t = mat_translation(0.0, 0.8, 0.5)
+    for r in (g, c):
+        r.update_items([(k, t, mat_inverse(t))])
+    assert g.bvh_info().grouped_items == 0
+    fg, fc = g.start(cam, cfg), c.render(cam, cfg)
+    assert lsb_stats(fg.image, fc.image)[0] >= 0.999 and np.array_equal(fg.objects, fc.objects) and np.array_equal(fg.depth, fc.depth)
+    assert (fg.stats.rays_closest, fg.stats.rays_shadow) == (fc.stats.rays_closest, fc.stats.rays_shadow)
+    o, d = random_rays(3000, 8, center=(0, 4, 0), radius=9.0)
+    sg, sc_ = g.shadow_probe(o, d, 12.0), c.shadow_probe(o, d, 12.0)
+    assert np.array_equal(sg["lit"], sc_["lit"])
+
+
 def test_one_process_multi_handle_rejects_bad_device_lists():
     fs, cam, cfg = abi.load_fixture("c1_spheres")
     with pytest.raises(RtxError):
