@@ -1028,7 +1028,8 @@ int render_frame_single(RtxScene* sc, const RtxCamera* cam, const RtxConfig* cfg
     memcpy(F.fog_color, cfg->fog_color, 12); F.debug_flags = cfg->debug_flags;
     // ray order inside a primary batch: one warp = 32 samples of ONE pixel (sub-pixel footprint: the lanes walk the same nodes,
     // hit the same material, and their shadow rays leave from the same spot) instead of one sample of an 8x4 tile: -4 % frame time
-    F.sample_group = 32; if (const char* e = getenv("RTX_SAMPLE_GROUP")) F.sample_group = std::max(1, atoi(e));
+    // (all samples of a pixel, up to 128, back to back: config-4 stand-in at 128 spp 204.3 -> 202.1 ms against groups of 32)
+    F.sample_group = 128; if (const char* e = getenv("RTX_SAMPLE_GROUP")) F.sample_group = std::max(1, atoi(e));
     F.sample_table = sc->sample_table.p; F.accum_c = sc->accum_c.p; F.accum_n = sc->accum_n.p; F.ids = sc->ids.p;
     h2d += sizeof(FrameDev);                                             // kernel parameters (camera + config)
 
