@@ -412,6 +412,9 @@ struct ShadeOut {
     uint32_t* skipped;                                          // RTX_OPT_SKIP_ZERO_SHADOW: count of untraced zero-contribution shadow rays
 };
 
+#ifndef RTX_SHADE_PREFETCH
+#define RTX_SHADE_PREFETCH 0                // measured: see DESIGN.md §6
+#endif
 #ifndef RTX_SHADE_MIN_BLOCKS
 #define RTX_SHADE_MIN_BLOCKS 8
 #endif
@@ -432,6 +435,15 @@ __global__ void __launch_bounds__(kShadeBlock, RTX_SHADE_MIN_BLOCKS) shade_kerne
             o = f3(ro.x, ro.y, ro.z); d = f3(rd.x, rd.y, rd.z); wgt = ro.w; pixel = __float_as_uint(rd.w);
             sample = m.x & 0xffffu; depth = (m.x >> 16) & 0xffu; rflags = m.x >> 24; path = m.y;
             h = hits[i];
+#if RTX_SHADE_PREFETCH
+            {   // the next ray of this thread: pull its queue entry and hit record towards L1 while this one is shaded
+                const uint32_t ni = i + gridDim.x * blockDim.x;
+                if (ni < n) {
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(q.o + q_base + ni)); asm volatile("prefetch.global.L1 [%0];" ::"l"(q.d + q_base + ni));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(q.m + q_base + ni)); asm volatile("prefetch.global.L1 [%0];" ::"l"(hits + ni));
+                }
+            }
+#endif
         }
         const bool hit = active && h.item != 0xFFFFFFFFu;
         if (active && !hit && (rflags & RF_ID_OWNER)) F.ids[pixel] = 0u;
