@@ -822,6 +822,44 @@ __device__ __forceinline__ bool group_hit_beyond_light(const SceneDev& S, float3
     return false;
 }
 
+// What a triangle hit means for the lane (closest: merge with the reference's order rule; any-hit: the ray is occluded).  In group
+// mode the item work (filter + exact slab key) happens here, once per item change.
+template <int MODE>
+__device__ __forceinline__ void lane_tri_hit(Lane& L, const SceneDev& S, float toi, uint32_t back, uint32_t prim, uint32_t face, uint32_t tri_item, bool for_shadow, uint32_t depth) {
+    if (L.cur_item & 0x80000000u) {                                       // triangle of the merged BLAS: item work only for a hit that would be taken
+        const bool cand = (MODE == UT_CLOSEST) ? (toi < L.tmax || (toi == L.tmax && L.bitem != 0xFFFFFFFFu)) : (toi <= L.tmax);
+        if (cand) {
+            if ((L.cur_item & 0x7FFFFFFFu) != tri_item) { group_item_key(S, tri_item, L.w.o, L.w.d, for_shadow, depth, L.cur_key); L.cur_item = 0x80000000u | tri_item; }
+            if (L.cur_key == L.cur_key) {
+                if (MODE == UT_CLOSEST) lane_accept(L, toi, L.cur_key, tri_item, prim, face, back);
+                else lane_any_hit(L, L.cur_key, tri_item, S);
+            }
+        }
+    } else if (MODE == UT_CLOSEST) lane_accept(L, toi, L.cur_key, L.cur_item, prim, face, back);
+    else if (toi <= L.tmax) lane_any_hit(L, L.cur_key, L.cur_item, S);
+}
+
+// Triangle round, two triangles at once: both records are loaded before either is tested, so the second load's latency hides
+// behind the first test (the triangle rounds wait for their loads, not for issue slots).
+template <int MODE, bool STATS>
+__device__ __forceinline__ void lane_leaf_tri2(Lane& L, const SceneDev& S, bool for_shadow, uint32_t depth, TravStats& st) {
+    const uint32_t t0 = bfind(L.tg.y);
+    L.tg.y &= ~(1u << t0);
+    const bool two = L.tg.y != 0u;
+    const uint32_t t1 = two ? bfind(L.tg.y) : t0;
+    L.tg.y &= ~(1u << t1);
+    const uint32_t p0 = L.tg.x + t0, p1 = L.tg.x + t1;
+    const float4* a = S.tris + (size_t)p0 * 3; const float4* b = S.tris + (size_t)p1 * 3;
+    const float4 a0 = __ldg(a), a1 = __ldg(a + 1), a2 = __ldg(a + 2), b0 = __ldg(b), b1 = __ldg(b + 1), b2 = __ldg(b + 2);
+    if (STATS) st.tris += two ? 2u : 1u;
+    float toi0, toi1; uint32_t back0, back1;
+    const bool h0 = tri_cast(f3(a0.x, a0.y, a0.z), f3(a1.x, a1.y, a1.z), f3(a2.x, a2.y, a2.z), L.r.o, L.r.d, toi0, back0);
+    const bool h1 = two && tri_cast(f3(b0.x, b0.y, b0.z), f3(b1.x, b1.y, b1.z), f3(b2.x, b2.y, b2.z), L.r.o, L.r.d, toi1, back1);
+    if (h0) lane_tri_hit<MODE>(L, S, toi0, back0, p0, __float_as_uint(a0.w), __float_as_uint(a1.w), for_shadow, depth);
+    // any-hit: the first hit ended the ray (its groups are gone); closest: the merge is order-independent
+    if (h1 && !(MODE == UT_ANY && L.bflags != 0u)) lane_tri_hit<MODE>(L, S, toi1, back1, p1, __float_as_uint(b0.w), __float_as_uint(b1.w), for_shadow, depth);
+}
+
 // WHICH: 0 = whatever the entry is; 1 = the caller knows it is a triangle (L.blas_base >= 0); 2 = an item of the TLAS.
 // The kernels run triangles and items in separate rounds: the two paths share no code, so a mixed round would execute
 // both at a fraction of the lanes each.

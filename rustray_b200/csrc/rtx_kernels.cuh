@@ -115,6 +115,9 @@ constexpr int kItemBatch = RTX_ITEM_BATCH;
 #define RTX_LEAF_BATCH_ANY RTX_LEAF_BATCH   // any-hit rays end at their first hit: postponing triangle tests costs node visits the hit would have saved
 #endif
 constexpr int kLeafBatchAny = RTX_LEAF_BATCH_ANY;
+#ifndef RTX_TRI_PAIR
+#define RTX_TRI_PAIR 0                      // triangle round loads both triangles before testing either (see lane_leaf_tri2)
+#endif
 #ifndef RTX_TRI_REPS
 #define RTX_TRI_REPS 2                      // triangles handled per lane in one triangle round
 #endif
@@ -168,10 +171,14 @@ __global__ void __launch_bounds__(kTraceBlock, RTX_MIN_BLOCKS) closest_kernel(Sc
                 if (mt != 0u && (__popc(mt) >= kLeafBatch || no_nodes)) {
                     if (STATS) { ph[3] += (lane == 0); ph[4] += want_tri; }
                     if (want_tri) {
+#if RTX_TRI_PAIR
+                        lane_leaf_tri2<UT_CLOSEST, STATS>(L, S, false, depth, st);
+#else
                         lane_leaf<UT_CLOSEST, STATS, 1>(L, stack, S, false, depth, st, n_items, n_sph);
 #pragma unroll
                         for (int rep = 1; rep < RTX_TRI_REPS; rep++)
                             if (L.tg.y != 0u && L.blas_base >= 0) lane_leaf<UT_CLOSEST, STATS, 1>(L, stack, S, false, depth, st, n_items, n_sph);
+#endif
                     }
                 }
                 if (mi != 0u && (__popc(mi) >= kItemBatch || no_nodes)) {
@@ -297,10 +304,14 @@ __global__ void __launch_bounds__(kTraceBlock, RTX_MIN_BLOCKS) shadow_any_kernel
                 if (mt != 0u && (__popc(mt) >= kLeafBatchAny || no_nodes)) {
                     if (STATS) { ph[3] += (lane == 0); ph[4] += want_tri; }
                     if (want_tri) {
+#if RTX_TRI_PAIR
+                        lane_leaf_tri2<UT_ANY, STATS>(L, S, true, depth, st);
+#else
                         lane_leaf<UT_ANY, STATS, 1>(L, stack, S, true, depth, st, n_items, n_sph);
 #pragma unroll
                         for (int rep = 1; rep < RTX_TRI_REPS; rep++)
                             if (L.tg.y != 0u && L.blas_base >= 0) lane_leaf<UT_ANY, STATS, 1>(L, stack, S, true, depth, st, n_items, n_sph);
+#endif
                     }
                 }
                 if (mi != 0u && (__popc(mi) >= kItemBatch || no_nodes)) {
