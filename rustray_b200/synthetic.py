@@ -297,9 +297,10 @@ def pbr_texture_set(n: int, rng, tint, metal: float = 0.0, rough=(0.3, 0.9), bri
     h = _fbm(n, rng)
     y, x = np.mgrid[0:n, 0:n]
     if bricks:
-        bw = n // bricks
-        row = y // (bw // 2)
-        mortar = ((y % (bw // 2)) < max(1, bw // 24)) | (((x + (row % 2) * (bw // 2)) % bw) < max(1, bw // 24))
+        bw = max(2, n // bricks)
+        hb = max(1, bw // 2)
+        row = y // hb
+        mortar = ((y % hb) < max(1, bw // 24)) | (((x + (row % 2) * hb) % bw) < max(1, bw // 24))
         h = np.where(mortar, h * 0.4, h)
     base = np.zeros((n, n, 4), dtype=np.uint8)
     base[..., :3] = np.clip((0.35 + 0.65 * h)[..., None] * np.asarray(tint, dtype=np.float32) * 255.0, 0, 255).astype(np.uint8)
